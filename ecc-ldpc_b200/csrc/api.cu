@@ -1,0 +1,503 @@
+// api.cu -- the C ABI of libldpc_b200.so (include/ldpc_b200.h). Host-side glue only; kernels live in
+// stream_engine.cu (any H, HBM-streaming), resident_engine.cu (quasi-cyclic, on-chip) and channel.cu.
+#include "common.cuh"
+#include "philox.cuh"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+namespace ldpc {
+
+static thread_local char g_err[512] = "";
+static int g_device = -1;
+static bool g_init = false;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return LDPC_B200_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return LDPC_B200_ENODEV;
+    return LDPC_B200_ECUDA;
+}
+
+static int require_init()
+{
+    if (!g_init) {
+        int rc = ldpc_b200_init(-1);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int upload_graph(ldpc_b200_code *c)
+{
+    DeviceGraph &g = c->g;
+    g.M = c->M; g.N = c->N; g.E = c->E; g.max_row_deg = c->max_row_deg; g.max_col_deg = c->max_col_deg;
+    size_t e = c->E > 0 ? c->E : 1;
+    LDPC_CUDA(cudaMalloc(&g.row_ptr, sizeof(int32_t) * (c->M + 1)));
+    LDPC_CUDA(cudaMalloc(&g.col_idx, sizeof(int32_t) * e));
+    LDPC_CUDA(cudaMalloc(&g.col_ptr, sizeof(int32_t) * (c->N + 1)));
+    LDPC_CUDA(cudaMalloc(&g.col_edge, sizeof(int32_t) * e));
+    LDPC_CUDA(cudaMemcpy(g.row_ptr, c->row_ptr.data(), sizeof(int32_t) * (c->M + 1), cudaMemcpyHostToDevice));
+    LDPC_CUDA(cudaMemcpy(g.col_ptr, c->col_ptr.data(), sizeof(int32_t) * (c->N + 1), cudaMemcpyHostToDevice));
+    if (c->E > 0) {
+        LDPC_CUDA(cudaMemcpy(g.col_idx, c->col_idx.data(), sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
+        LDPC_CUDA(cudaMemcpy(g.col_edge, c->col_edge.data(), sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// Fills the CSC side and the degree maxima from row_ptr / col_idx.
+static int finish_code(ldpc_b200_code *c)
+{
+    int M = c->M, N = c->N;
+    c->E = c->row_ptr[M];
+    c->col_ptr.assign(N + 1, 0);
+    c->col_edge.assign(c->E > 0 ? c->E : 1, 0);
+    c->max_row_deg = 0;
+    for (int m = 0; m < M; m++) {
+        int d = c->row_ptr[m + 1] - c->row_ptr[m];
+        c->max_row_deg = std::max(c->max_row_deg, d);
+        for (int e = c->row_ptr[m]; e < c->row_ptr[m + 1]; e++) c->col_ptr[c->col_idx[e] + 1]++;
+    }
+    c->max_col_deg = 0;
+    for (int j = 0; j < N; j++) {
+        c->max_col_deg = std::max(c->max_col_deg, c->col_ptr[j + 1]);
+        c->col_ptr[j + 1] += c->col_ptr[j];
+    }
+    std::vector<int32_t> fill(N, 0);
+    for (int m = 0; m < M; m++)
+        for (int e = c->row_ptr[m]; e < c->row_ptr[m + 1]; e++) {
+            int j = c->col_idx[e];
+            c->col_edge[c->col_ptr[j] + fill[j]++] = e;
+        }
+    return 0;
+}
+
+static int pick_engine(const ldpc_b200_decoder *d)
+{
+    if (d->engine == LDPC_B200_ENGINE_STREAM) return LDPC_B200_ENGINE_STREAM;
+    if (resident_supports(d)) return LDPC_B200_ENGINE_RESIDENT;
+    return LDPC_B200_ENGINE_STREAM;
+}
+
+static int ensure_staging(ldpc_b200_decoder *d)
+{
+    if (d->d_bits) return 0;
+    int N = d->code->N;
+    size_t B = (size_t)d->max_batch;
+    LDPC_CUDA(cudaMalloc(&d->d_in, B * N * sizeof(double)));
+    LDPC_CUDA(cudaMalloc(&d->d_bits, B * words_per_frame(N) * sizeof(uint32_t)));
+    LDPC_CUDA(cudaMalloc(&d->d_iters, B * sizeof(int32_t)));
+    LDPC_CUDA(cudaMalloc(&d->d_conv, B));
+    LDPC_CUDA(cudaMalloc(&d->d_counters, 8 * sizeof(uint64_t)));
+    return 0;
+}
+
+static int decode_dispatch(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                           bool llr_is_double, uint32_t *d_bits, int32_t *d_iters, uint8_t *d_conv)
+{
+    if (pick_engine(d) == LDPC_B200_ENGINE_RESIDENT)
+        return resident_decode(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits, d_iters, d_conv);
+    return stream_decode(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits, d_iters, d_conv, nullptr, nullptr);
+}
+
+static void begin_timing(ldpc_b200_decoder *d)
+{
+    d->launches = 0;
+    cudaEventRecord(d->ev0, d->stream);
+}
+
+static void end_timing(ldpc_b200_decoder *d)
+{
+    cudaEventRecord(d->ev1, d->stream);
+    d->timing_pending = true;
+    d->last_launches = d->launches;
+}
+
+static int finish_timing(ldpc_b200_decoder *d)
+{
+    if (d->timing_pending) {
+        LDPC_CUDA(cudaEventSynchronize(d->ev1));
+        float ms = 0.f;
+        LDPC_CUDA(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+        d->last_ms = ms;
+        d->timing_pending = false;
+    }
+    return 0;
+}
+
+static void channel_params(double ebn0_db, int k_info, int n_tx, float *sigma, float *scale)
+{
+    // sigma^2 = 1 / (2 R Eb/N0), R = k_info / n_tx (pinned statistically by NOTES.txt:3,8,13)
+    double R = (double)k_info / (double)n_tx;
+    double s2 = 1.0 / (2.0 * R * pow(10.0, ebn0_db / 10.0));
+    *sigma = (float)sqrt(s2);
+    *scale = (float)(2.0 / s2);
+}
+
+}  // namespace ldpc
+
+using namespace ldpc;
+
+extern "C" {
+
+int ldpc_b200_abi_version(void) { return LDPC_B200_ABI_VERSION; }
+const char *ldpc_b200_last_error(void) { return g_err; }
+
+int ldpc_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ldpc_b200_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libldpc_b200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return LDPC_B200_ENODEV;
+    }
+    if (device >= n) { set_error("device %d out of range (%d devices)", device, n); return LDPC_B200_EINVAL; }
+    if (device >= 0) LDPC_CUDA(cudaSetDevice(device));
+    LDPC_CUDA(cudaGetDevice(&g_device));
+    LDPC_CUDA(cudaFree(0));
+    g_init = true;
+    return 0;
+}
+
+void ldpc_b200_shutdown(void) { g_init = false; }
+
+int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_t *col_idx, ldpc_b200_code_t **out)
+{
+    if (!out || M < 0 || N <= 0 || !row_ptr || (!col_idx && row_ptr[M] > 0)) { set_error("code_create_csr: bad arguments"); return LDPC_B200_EINVAL; }
+    if (row_ptr[0] != 0) { set_error("code_create_csr: row_ptr[0] must be 0"); return LDPC_B200_EINVAL; }
+    for (int m = 0; m < M; m++) {
+        if (row_ptr[m + 1] < row_ptr[m]) { set_error("code_create_csr: row_ptr not monotone at row %d", m); return LDPC_B200_EINVAL; }
+        for (int e = row_ptr[m]; e < row_ptr[m + 1]; e++) {
+            if (col_idx[e] < 0 || col_idx[e] >= N) { set_error("code_create_csr: column %d out of range in row %d", col_idx[e], m); return LDPC_B200_EINVAL; }
+            if (e > row_ptr[m] && col_idx[e] <= col_idx[e - 1]) { set_error("code_create_csr: columns of row %d not strictly ascending", m); return LDPC_B200_EINVAL; }
+        }
+    }
+    int rc = require_init();
+    if (rc) return rc;
+    ldpc_b200_code *c = new (std::nothrow) ldpc_b200_code();
+    if (!c) return LDPC_B200_ENOMEM;
+    c->M = M; c->N = N;
+    c->row_ptr.assign(row_ptr, row_ptr + M + 1);
+    c->col_idx.assign(col_idx, col_idx + row_ptr[M]);
+    finish_code(c);
+    c->device = g_device;
+    rc = upload_graph(c);
+    if (rc) { ldpc_b200_code_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts, ldpc_b200_code_t **out)
+{
+    if (!out || sz <= 0 || brows <= 0 || bcols <= 0 || !shifts) { set_error("code_create_qc: bad arguments"); return LDPC_B200_EINVAL; }
+    for (int i = 0; i < brows * bcols; i++)
+        if (shifts[i] < -1 || shifts[i] >= sz) { set_error("code_create_qc: shift %d out of range [-1, %d)", shifts[i], sz); return LDPC_B200_EINVAL; }
+    int rc = require_init();
+    if (rc) return rc;
+    ldpc_b200_code *c = new (std::nothrow) ldpc_b200_code();
+    if (!c) return LDPC_B200_ENOMEM;
+    c->M = brows * sz; c->N = bcols * sz;
+    c->sz = sz; c->brows = brows; c->bcols = bcols;
+    c->shifts.assign(shifts, shifts + brows * bcols);
+    // QuasiCyclic.hs:19-25: row r*sz+i has a one in column c*sz + (i+k) mod sz for every block with shift k.
+    c->row_ptr.assign(c->M + 1, 0);
+    for (int r = 0; r < brows; r++)
+        for (int i = 0; i < sz; i++) {
+            int m = r * sz + i;
+            for (int b = 0; b < bcols; b++) {
+                int k = shifts[r * bcols + b];
+                if (k >= 0) c->col_idx.push_back(b * sz + (i + k) % sz);
+            }
+            c->row_ptr[m + 1] = (int32_t)c->col_idx.size();
+        }
+    finish_code(c);
+    c->device = g_device;
+    c->resident_kind = resident_kind_for(c);
+    rc = upload_graph(c);
+    if (rc) { ldpc_b200_code_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
+{
+    if (!c) return;
+    cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
+    delete c;
+}
+
+int ldpc_b200_code_info(const ldpc_b200_code_t *c, int *M, int *N, int *E, int *qc_sz)
+{
+    if (!c) { set_error("code_info: null code"); return LDPC_B200_EINVAL; }
+    if (M) *M = c->M;
+    if (N) *N = c->N;
+    if (E) *E = c->E;
+    if (qc_sz) *qc_sz = c->sz;
+    return 0;
+}
+
+int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precision, int max_batch, ldpc_b200_decoder_t **out)
+{
+    if (!code || !out || max_batch <= 0) { set_error("decoder_create: bad arguments"); return LDPC_B200_EINVAL; }
+    if (algo != LDPC_B200_ALGO_SPA && algo != LDPC_B200_ALGO_MINSUM) { set_error("decoder_create: unknown algo %d", algo); return LDPC_B200_EINVAL; }
+    if (precision != LDPC_B200_PREC_FP64 && precision != LDPC_B200_PREC_FP32) { set_error("decoder_create: unknown precision %d", precision); return LDPC_B200_EINVAL; }
+    int rc = require_init();
+    if (rc) return rc;
+    ldpc_b200_decoder *d = new (std::nothrow) ldpc_b200_decoder();
+    if (!d) return LDPC_B200_ENOMEM;
+    d->code = code; d->algo = algo; d->precision = precision; d->max_batch = max_batch;
+    LDPC_CUDA(cudaSetDevice(code->device));
+    LDPC_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    LDPC_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    LDPC_CUDA(cudaEventCreate(&d->ev0));
+    LDPC_CUDA(cudaEventCreate(&d->ev1));
+    *out = d;
+    return 0;
+}
+
+int ldpc_b200_decoder_set_engine(ldpc_b200_decoder_t *d, int engine)
+{
+    if (!d || engine < 0 || engine > 2) { set_error("set_engine: bad arguments"); return LDPC_B200_EINVAL; }
+    if (engine == LDPC_B200_ENGINE_RESIDENT && !resident_supports(d)) {
+        set_error("RESIDENT engine has no specialisation for this code / algorithm / precision");
+        return LDPC_B200_EUNSUPPORTED;
+    }
+    d->engine = engine;
+    return 0;
+}
+
+int ldpc_b200_decoder_engine(const ldpc_b200_decoder_t *d) { return d ? pick_engine(d) : LDPC_B200_EINVAL; }
+
+void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
+{
+    if (!d) return;
+    cudaStreamSynchronize(d->stream);
+    stream_free(d);
+    cudaFree(d->d_in); cudaFree(d->d_bits); cudaFree(d->d_iters); cudaFree(d->d_conv); cudaFree(d->d_counters);
+    if (d->h_pinned) cudaFreeHost(d->h_pinned);
+    cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
+    cudaStreamDestroy(d->stream); cudaStreamDestroy(d->copy_stream);
+    delete d;
+}
+
+void *ldpc_b200_decoder_stream(ldpc_b200_decoder_t *d) { return d ? (void *)d->stream : nullptr; }
+
+int ldpc_b200_decoder_sync(ldpc_b200_decoder_t *d)
+{
+    if (!d) { set_error("decoder_sync: null decoder"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaStreamSynchronize(d->stream));
+    return finish_timing(d);
+}
+
+int ldpc_b200_decoder_last_timing(ldpc_b200_decoder_t *d, double *kernel_ms, int64_t *launches)
+{
+    if (!d) { set_error("last_timing: null decoder"); return LDPC_B200_EINVAL; }
+    int rc = finish_timing(d);
+    if (rc) return rc;
+    if (kernel_ms) *kernel_ms = d->last_ms;
+    if (launches) *launches = d->last_launches;
+    return 0;
+}
+
+int ldpc_b200_decode_device(ldpc_b200_decoder_t *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                            uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_converged)
+{
+    if (!d || max_iters < 0 || n_frames < 0 || (n_frames && (!d_llr || !d_bits_packed))) { set_error("decode_device: bad arguments"); return LDPC_B200_EINVAL; }
+    if (n_frames > d->max_batch) { set_error("decode_device: n_frames %d > max_batch %d", n_frames, d->max_batch); return LDPC_B200_EINVAL; }
+    if (n_frames == 0) return 0;
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    begin_timing(d);
+    rc = decode_dispatch(d, max_iters, early_exit, n_frames, d_llr, d->precision == LDPC_B200_PREC_FP64, d_bits_packed,
+                         d_iters ? d_iters : d->d_iters, d_converged ? d_converged : d->d_conv);
+    end_timing(d);
+    return rc;
+}
+
+// Shared body of the two host-buffer entry points.
+static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const void *llr, bool is_double,
+                       uint8_t *bits_bytes, uint32_t *bits_packed, int32_t *iters, uint8_t *converged)
+{
+    if (!d || max_iters < 0 || n_frames < 0 || (n_frames && (!llr || (!bits_bytes && !bits_packed)))) { set_error("decode: bad arguments"); return LDPC_B200_EINVAL; }
+    if (n_frames == 0) return 0;
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    int N = d->code->N, W = words_per_frame(N);
+    size_t in_es = is_double ? sizeof(double) : sizeof(float);
+    uint8_t *d_bytes = nullptr;
+    if (bits_bytes) LDPC_CUDA(cudaMalloc(&d_bytes, (size_t)std::min(n_frames, d->max_batch) * N));
+    double total_ms = 0.0;
+    int64_t total_launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += d->max_batch) {
+        int F = std::min(d->max_batch, n_frames - f0);
+        LDPC_CUDA(cudaMemcpyAsync(d->d_in, (const char *)llr + (size_t)f0 * N * in_es, (size_t)F * N * in_es, cudaMemcpyHostToDevice, d->stream));
+        begin_timing(d);
+        rc = decode_dispatch(d, max_iters, 1, F, d->d_in, is_double, d->d_bits, d->d_iters, d->d_conv);
+        if (rc) break;
+        if (bits_bytes) {
+            rc = unpack_bits(d, F, d->d_bits, d_bytes);
+            if (rc) break;
+        }
+        end_timing(d);
+        if (bits_bytes) LDPC_CUDA(cudaMemcpyAsync(bits_bytes + (size_t)f0 * N, d_bytes, (size_t)F * N, cudaMemcpyDeviceToHost, d->stream));
+        if (bits_packed) LDPC_CUDA(cudaMemcpyAsync(bits_packed + (size_t)f0 * W, d->d_bits, (size_t)F * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+        if (iters) LDPC_CUDA(cudaMemcpyAsync(iters + f0, d->d_iters, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+        if (converged) LDPC_CUDA(cudaMemcpyAsync(converged + f0, d->d_conv, (size_t)F, cudaMemcpyDeviceToHost, d->stream));
+        LDPC_CUDA(cudaStreamSynchronize(d->stream));
+        finish_timing(d);
+        total_ms += d->last_ms;
+        total_launches += d->last_launches;
+    }
+    if (d_bytes) cudaFree(d_bytes);
+    d->last_ms = total_ms;
+    d->last_launches = total_launches;
+    return rc;
+}
+
+int ldpc_b200_decode(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const double *llr, uint8_t *bits,
+                     int32_t *iters, uint8_t *converged)
+{
+    return decode_host(d, max_iters, n_frames, llr, true, bits, nullptr, iters, converged);
+}
+
+int ldpc_b200_decode_f32(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const float *llr, uint32_t *bits_packed,
+                         int32_t *iters, uint8_t *converged)
+{
+    return decode_host(d, max_iters, n_frames, llr, false, nullptr, bits_packed, iters, converged);
+}
+
+int ldpc_b200_decode_trace(ldpc_b200_decoder_t *d, int max_iters, const double *llr, double *c2v, double *lam,
+                           int32_t *iters, uint8_t *bits, uint8_t *converged)
+{
+    if (!d || max_iters < 0 || !llr) { set_error("decode_trace: bad arguments"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    int N = d->code->N, W = words_per_frame(N);
+    LDPC_CUDA(cudaMemcpyAsync(d->d_in, llr, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    begin_timing(d);
+    rc = stream_decode(d, max_iters, 1, 1, d->d_in, true, d->d_bits, d->d_iters, d->d_conv, c2v, lam);
+    end_timing(d);
+    if (rc) return rc;
+    std::vector<uint32_t> packed(W);
+    int32_t it = 0; uint8_t cv = 0;
+    LDPC_CUDA(cudaMemcpyAsync(packed.data(), d->d_bits, W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    LDPC_CUDA(cudaMemcpyAsync(&it, d->d_iters, sizeof it, cudaMemcpyDeviceToHost, d->stream));
+    LDPC_CUDA(cudaMemcpyAsync(&cv, d->d_conv, 1, cudaMemcpyDeviceToHost, d->stream));
+    LDPC_CUDA(cudaStreamSynchronize(d->stream));
+    finish_timing(d);
+    if (bits) for (int j = 0; j < N; j++) bits[j] = (packed[j >> 5] >> (j & 31)) & 1u;
+    if (iters) *iters = it;
+    if (converged) *converged = cv;
+    return 0;
+}
+
+int ldpc_b200_generate_llr(ldpc_b200_decoder_t *d, double ebn0_db, int k_info, int n_tx, uint64_t seed,
+                           uint64_t first_frame, int n_frames, const uint32_t *d_codewords, void *d_llr)
+{
+    if (!d || !d_llr || n_frames < 0 || k_info <= 0 || n_tx <= 0 || n_tx > d->code->N) { set_error("generate_llr: bad arguments"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    float sigma, scale;
+    channel_params(ebn0_db, k_info, n_tx, &sigma, &scale);
+    return channel_generate(d, sigma, scale, n_tx, seed, first_frame, n_frames, d_codewords, d_llr);
+}
+
+int ldpc_b200_simulate_device(ldpc_b200_decoder_t *d, int max_iters, int early_exit, double ebn0_db, int k_info, int n_tx,
+                              uint64_t seed, uint64_t first_frame, uint64_t n_frames, uint64_t *d_counters)
+{
+    if (!d || !d_counters || max_iters < 0 || k_info <= 0 || k_info > d->code->N || n_tx <= 0 || n_tx > d->code->N) { set_error("simulate: bad arguments"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    float sigma, scale;
+    channel_params(ebn0_db, k_info, n_tx, &sigma, &scale);
+    begin_timing(d);
+    if (pick_engine(d) == LDPC_B200_ENGINE_RESIDENT) {
+        rc = resident_simulate(d, max_iters, early_exit, sigma, scale, k_info, n_tx, seed, first_frame, n_frames, d_counters);
+    } else {
+        // generate -> decode -> count, one max_batch at a time; frames are generated in the decoder's precision
+        // straight into the staging buffer.
+        for (uint64_t f0 = 0; f0 < n_frames && !rc; f0 += (uint64_t)d->max_batch) {
+            int F = (int)std::min<uint64_t>((uint64_t)d->max_batch, n_frames - f0);
+            rc = channel_generate(d, sigma, scale, n_tx, seed, first_frame + f0, F, nullptr, d->d_in);
+            if (!rc) rc = stream_decode(d, max_iters, early_exit, F, d->d_in, d->precision == LDPC_B200_PREC_FP64, d->d_bits, d->d_iters, d->d_conv, nullptr, nullptr);
+            if (!rc) rc = channel_count(d, F, k_info, d->d_bits, d->d_iters, d->d_conv, d_counters);
+        }
+    }
+    end_timing(d);
+    return rc;
+}
+
+int ldpc_b200_simulate(ldpc_b200_decoder_t *d, int max_iters, int early_exit, double ebn0_db, int k_info, int n_tx,
+                       uint64_t seed, uint64_t first_frame, uint64_t n_frames, ldpc_b200_counters_t *out)
+{
+    if (!d || !out) { set_error("simulate: bad arguments"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    LDPC_CUDA(cudaMemsetAsync(d->d_counters, 0, 8 * sizeof(uint64_t), d->stream));
+    rc = ldpc_b200_simulate_device(d, max_iters, early_exit, ebn0_db, k_info, n_tx, seed, first_frame, n_frames, d->d_counters);
+    if (rc) return rc;
+    uint64_t h[8];
+    LDPC_CUDA(cudaMemcpyAsync(h, d->d_counters, sizeof h, cudaMemcpyDeviceToHost, d->stream));
+    LDPC_CUDA(cudaStreamSynchronize(d->stream));
+    finish_timing(d);
+    out->frames += h[0]; out->frame_errors += h[1]; out->bit_errors += h[2]; out->sum_iters += h[3]; out->unconverged += h[4];
+    out->kernel_ms += d->last_ms;
+    return 0;
+}
+
+int ldpc_b200_malloc(void **p, uint64_t bytes)
+{
+    if (!p) return LDPC_B200_EINVAL;
+    int rc = require_init();
+    if (rc) return rc;
+    LDPC_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    return 0;
+}
+int ldpc_b200_free(void *p) { LDPC_CUDA(cudaFree(p)); return 0; }
+int ldpc_b200_malloc_host(void **p, uint64_t bytes)
+{
+    if (!p) return LDPC_B200_EINVAL;
+    int rc = require_init();
+    if (rc) return rc;
+    LDPC_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return 0;
+}
+int ldpc_b200_free_host(void *p) { LDPC_CUDA(cudaFreeHost(p)); return 0; }
+int ldpc_b200_memcpy_h2d(void *dst, const void *src, uint64_t bytes) { LDPC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int ldpc_b200_memcpy_d2h(void *dst, const void *src, uint64_t bytes) { LDPC_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int ldpc_b200_memset(void *p, int value, uint64_t bytes) { LDPC_CUDA(cudaMemset(p, value, bytes)); return 0; }
+
+int ldpc_b200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    if (!ctr || !key || !out) return LDPC_B200_EINVAL;
+    Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    for (int i = 0; i < 4; i++) out[i] = r.v[i];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// common.cuh -- shared host-side structures of libldpc_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/ldpc_b200.h"
+
+namespace ldpc {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define LDPC_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (call);                                                     \
+        if (_e != cudaSuccess) return ldpc::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// Device-resident H. Edge order = reference order: row-major, ascending column
+// (the order Reference/Orig.hs:82-92 visits the ones of H).
+struct DeviceGraph {
+    int M = 0, N = 0, E = 0, max_row_deg = 0, max_col_deg = 0;
+    int32_t *row_ptr = nullptr;   // [M+1]
+    int32_t *col_idx = nullptr;   // [E]  edge -> variable
+    int32_t *col_ptr = nullptr;   // [N+1]
+    int32_t *col_edge = nullptr;  // [E]  edges of variable j, ascending check index
+};
+
+}  // namespace ldpc
+
+struct ldpc_b200_code {
+    int M = 0, N = 0, E = 0;
+    std::vector<int32_t> row_ptr, col_idx, col_ptr, col_edge;
+    int max_row_deg = 0, max_col_deg = 0;
+    // quasi-cyclic description (sz == 0 when the code was given as CSR)
+    int sz = 0, brows = 0, bcols = 0;
+    std::vector<int32_t> shifts;
+    int device = -1;
+    ldpc::DeviceGraph g;          // device copy
+    int resident_kind = 0;        // 0 = none, else id of the compiled RESIDENT specialisation
+};
+
+namespace ldpc {
+
+struct StreamBuffers {
+    void *L = nullptr, *lam = nullptr, *ne = nullptr;   // [N][Bp], [N][Bp], [E][Bp] in T
+    int32_t *iters = nullptr;    // [Bp]
+    uint8_t *state = nullptr;    // [Bp] 0 = running, 1 = converged, 2 = gave up (fallback to L)
+    uint8_t *unsat = nullptr;    // [Bp]
+    int *active = nullptr;       // [1] frames still running
+    int Bp = 0;
+};
+
+}  // namespace ldpc
+
+struct ldpc_b200_decoder {
+    const ldpc_b200_code *code = nullptr;
+    int algo = 1, precision = 1, max_batch = 0, engine = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ldpc::StreamBuffers sb;
+    // staging for host-buffer calls
+    void *d_in = nullptr;        // max_batch x N (double)
+    uint32_t *d_bits = nullptr;  // max_batch x ceil(N/32)
+    int32_t *d_iters = nullptr;
+    uint8_t *d_conv = nullptr;
+    uint64_t *d_counters = nullptr;   // 5 x u64
+    void *h_pinned = nullptr;    // pinned staging
+    size_t h_pinned_bytes = 0;
+    double last_ms = 0.0;
+    int64_t last_launches = 0;
+    int64_t launches = 0;        // running count within a call
+    bool timing_pending = false;
+};
+
+namespace ldpc {
+
+inline int words_per_frame(int N) { return (N + 31) / 32; }
+inline size_t elem_size(int precision) { return precision == LDPC_B200_PREC_FP64 ? 8 : 4; }
+
+// ---- stream engine (stream_engine.cu) ----
+int stream_alloc(ldpc_b200_decoder *d);
+void stream_free(ldpc_b200_decoder *d);
+// d_llr: n_frames x N in T (frame-major). Runs the whole decode; outputs are frame-major device buffers.
+int stream_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                  bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv,
+                  double *h_trace_c2v, double *h_trace_lam);
+
+// ---- resident engine (resident_engine.cu) ----
+int resident_kind_for(const ldpc_b200_code *c);          // 0 if no specialisation matches
+bool resident_supports(const ldpc_b200_decoder *d);
+int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv);
+int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float sigma, float llr_scale,
+                      int k_info, int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
+                      uint64_t *d_counters);
+
+// ---- channel (channel.cu) ----
+int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_tx, uint64_t seed,
+                     uint64_t first_frame, int n_frames, const uint32_t *d_codewords, void *d_llr);
+int channel_count(ldpc_b200_decoder *d, int n_frames, int k_info, const uint32_t *d_bits_packed,
+                  const int32_t *d_iters, const uint8_t *d_conv, uint64_t *d_counters);
+int unpack_bits(ldpc_b200_decoder *d, int n_frames, const uint32_t *d_bits_packed, uint8_t *d_bytes);
+
+}  // namespace ldpc

@@ -1,0 +1,304 @@
+// stream_engine.cu -- STREAM engine: flooding BP for ANY parity-check matrix, messages in HBM.
+//
+// This engine states the reference algorithm in its own operation order, so the fp64 instance is the
+// message-level verification mode (ldpc_b200_decode_trace) and the fall-back for codes the RESIDENT
+// engine has no specialisation for.
+//
+// Layout (frame-minor, so every access is coalesced over the frames of a batch):
+//   L  [N][Bp]   channel LLRs                 lam [N][Bp]  posteriors
+//   ne [E][Bp]   check->variable messages in reference edge order (row-major, ascending column)
+// One thread = one (check, frame) in the check-node kernel, one (variable, frame) in the variable-node
+// kernel.  Algorithmic traffic per frame and iteration is the reference's state model, 3E + 3N words
+// (SURVEY.md 8d): CN reads E ne + gathers lam, writes E ne; VN reads E ne + N L, writes N lam.
+//
+// Reference lines restated: driver loop Orig.hs:58-71 / Min.hs:54-67; syndrome Orig.hs:73-78;
+// SPA check update Orig.hs:81-92 with atanh' of Utils.hs:113-117; min-sum check update Min.hs:75-87;
+// variable update Orig.hs:95-98 (right fold: last row first, starting from the channel LLR).
+#include "common.cuh"
+#include <math.h>
+
+namespace ldpc {
+
+static constexpr int TPB = 128;   // threads per block along the frame axis
+
+template <typename T> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
+    static __device__ __forceinline__ double atanh_(double x) { return atanh(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <> struct Num<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float atanh_(float x) { return atanhf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+
+// llr [F][N] (frame-major, TIn) -> L, lam [N][Bp] (frame-minor, T). 32x32 tile transpose through smem.
+template <typename T, typename TIn>
+__global__ void k_load(const TIn *__restrict__ llr, T *__restrict__ L, T *__restrict__ lam, int N, int F, int Bp)
+{
+    __shared__ T tile[32][33];
+    int j0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int f = f0 + r, j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (f < F && j < N) ? (T)llr[(size_t)f * N + j] : (T)0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int j = j0 + r, f = f0 + threadIdx.x;
+        if (j < N && f < Bp) {
+            T v = tile[threadIdx.x][r];
+            L[(size_t)j * Bp + f] = v;
+            lam[(size_t)j * Bp + f] = v;
+        }
+    }
+}
+
+// Orig.hs:73-78: c_hat = hard lam (x > 0); H * c_hat over GF(2). One thread per (check, frame).
+template <typename T>
+__global__ void k_syndrome(DeviceGraph g, const T *__restrict__ lam, const uint8_t *__restrict__ state,
+                           uint8_t *__restrict__ unsat, int F, int Bp, int skip_done)
+{
+    int f = blockIdx.x * TPB + threadIdx.x, m = blockIdx.y;
+    if (f >= F) return;
+    if (skip_done && state[f]) return;
+    int p = 0;
+    for (int e = g.row_ptr[m]; e < g.row_ptr[m + 1]; e++) p ^= (lam[(size_t)g.col_idx[e] * Bp + f] > (T)0);
+    if (p) unsat[f] = 1;
+}
+
+// Orig.hs:68-70: syndrome ok -> stop with lam; n >= maxIterations -> stop with orig_lam.
+__global__ void k_status(uint8_t *__restrict__ state, uint8_t *__restrict__ unsat, int32_t *__restrict__ iters,
+                         int *__restrict__ active, int n, int max_iters, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    int running = 0;
+    if (f < F) {
+        if (state[f] == 0) {
+            if (!unsat[f]) { state[f] = 1; iters[f] = n; }
+            else if (n >= max_iters) { state[f] = 2; iters[f] = n; }
+            else running = 1;
+        }
+        unsat[f] = 0;
+    }
+    unsigned b = __ballot_sync(0xffffffffu, running);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(active, __popc(b));
+}
+
+// Hard decision of the frames that stopped at iteration n: lam if converged, L on fallback.
+// Thread = (32-bit word, frame); reads are coalesced over frames.
+template <typename T>
+__global__ void k_hard(const T *__restrict__ lam, const T *__restrict__ L, const uint8_t *__restrict__ state,
+                       const int32_t *__restrict__ iters, uint32_t *__restrict__ bits, int n, int N, int F, int Bp)
+{
+    int f = blockIdx.x * TPB + threadIdx.x, w = blockIdx.y;
+    if (f >= F) return;
+    uint8_t s = state[f];
+    if (s == 0 || iters[f] != n) return;
+    const T *src = (s == 1) ? lam : L;
+    uint32_t word = 0;
+    int j0 = w * 32;
+#pragma unroll 8
+    for (int b = 0; b < 32; b++) {
+        int j = j0 + b;
+        if (j < N && src[(size_t)j * Bp + f] > (T)0) word |= (1u << b);
+    }
+    bits[(size_t)f * ((N + 31) / 32) + w] = word;
+}
+
+// Utils.hs:113-117
+template <typename T>
+__device__ __forceinline__ T atanh_prime(T x)
+{
+    T y = Num<T>::atanh_(x);
+    if (isinf(y)) return x > (T)0 ? (T)18.714973875118524 : (T)-18.714973875118524;
+    return y;
+}
+
+// Check-node update, one thread per (check, frame).
+template <typename T, int ALGO, int MAXD>
+__global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ ne,
+                     const uint8_t *__restrict__ state, int F, int Bp, int skip_done)
+{
+    int f = blockIdx.x * TPB + threadIdx.x, m = blockIdx.y;
+    if (f >= F) return;
+    if (skip_done && state[f]) return;
+    int b = g.row_ptr[m], d = g.row_ptr[m + 1] - b;
+    if (ALGO == LDPC_B200_ALGO_SPA) {
+        // Orig.hs:86-91: tanh(-((lam_j - ne[m,j]) / 2)) per edge, leave-one-out LEFT fold of (*) from 1.
+        T t[MAXD];
+        for (int k = 0; k < d; k++) {
+            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            t[k] = Num<T>::tanh_(-(v / (T)2));
+        }
+        for (int k = 0; k < d; k++) {
+            T p = (T)1;
+            for (int q = 0; q < d; q++) if (q != k) p = Num<T>::mul(p, t[q]);
+            ne[(size_t)(b + k) * Bp + f] = (T)-2 * atanh_prime<T>(p);
+        }
+    } else {
+        // Min.hs:79-89 in two-minimum form (Model.hs:326-343): exact, because min and sign products are exact.
+        T m1 = Num<T>::inf(), m2 = Num<T>::inf();
+        int neg = 0;
+        for (int k = 0; k < d; k++) {
+            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T a = Num<T>::abs_(x);
+            if (a < m1) { m2 = m1; m1 = a; } else if (a < m2) m2 = a;
+            neg ^= (x < (T)0);
+        }
+        for (int k = 0; k < d; k++) {
+            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T mag = (Num<T>::abs_(x) == m1) ? m2 : m1;
+            T v = (neg ^ (x < (T)0)) ? -mag : mag;
+            ne[(size_t)(b + k) * Bp + f] = Num<T>::mul((T)-0.75, v);
+        }
+    }
+}
+
+// Orig.hs:95-98: lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))). One thread per (variable, frame).
+template <typename T>
+__global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict__ ne, T *__restrict__ lam,
+                     const uint8_t *__restrict__ state, int F, int Bp, int skip_done)
+{
+    int f = blockIdx.x * TPB + threadIdx.x, j = blockIdx.y;
+    if (f >= F) return;
+    if (skip_done && state[f]) return;
+    T acc = L[(size_t)j * Bp + f];
+    for (int q = g.col_ptr[j + 1] - 1; q >= g.col_ptr[j]; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
+    lam[(size_t)j * Bp + f] = acc;
+}
+
+__global__ void k_finish(const uint8_t *__restrict__ state, const int32_t *__restrict__ iters,
+                         int32_t *__restrict__ out_iters, uint8_t *__restrict__ out_conv, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    if (out_iters) out_iters[f] = iters[f];
+    if (out_conv) out_conv[f] = state[f] == 1;
+}
+
+int stream_alloc(ldpc_b200_decoder *d)
+{
+    StreamBuffers &s = d->sb;
+    if (s.L) return 0;
+    const ldpc_b200_code *c = d->code;
+    int Bp = ((d->max_batch + TPB - 1) / TPB) * TPB;
+    size_t es = elem_size(d->precision);
+    s.Bp = Bp;
+    LDPC_CUDA(cudaMalloc(&s.L, (size_t)c->N * Bp * es));
+    LDPC_CUDA(cudaMalloc(&s.lam, (size_t)c->N * Bp * es));
+    LDPC_CUDA(cudaMalloc(&s.ne, (size_t)(c->E > 0 ? c->E : 1) * Bp * es));
+    LDPC_CUDA(cudaMalloc(&s.iters, sizeof(int32_t) * Bp));
+    LDPC_CUDA(cudaMalloc(&s.state, Bp));
+    LDPC_CUDA(cudaMalloc(&s.unsat, Bp));
+    LDPC_CUDA(cudaMalloc(&s.active, sizeof(int)));
+    return 0;
+}
+
+void stream_free(ldpc_b200_decoder *d)
+{
+    StreamBuffers &s = d->sb;
+    cudaFree(s.L); cudaFree(s.lam); cudaFree(s.ne); cudaFree(s.iters); cudaFree(s.state); cudaFree(s.unsat);
+    cudaFree(s.active);
+    s = StreamBuffers();
+}
+
+template <typename T, int ALGO>
+static int launch_cn(ldpc_b200_decoder *d, dim3 grid, int F, int skip_done)
+{
+    const DeviceGraph &g = d->code->g;
+    StreamBuffers &s = d->sb;
+    if (g.max_row_deg <= 8)
+        k_cn<T, ALGO, 8><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+    else if (g.max_row_deg <= 32)
+        k_cn<T, ALGO, 32><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+    else
+        k_cn<T, ALGO, 128><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+    d->launches++;
+    return 0;
+}
+
+template <typename T>
+static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, int F, const void *d_llr,
+                           bool llr_is_double, uint32_t *d_bits, int32_t *d_iters, uint8_t *d_conv,
+                           double *h_c2v, double *h_lam)
+{
+    const ldpc_b200_code *c = d->code;
+    const DeviceGraph &g = c->g;
+    StreamBuffers &s = d->sb;
+    cudaStream_t st = d->stream;
+    int Bp = s.Bp, N = c->N, E = c->E, M = c->M;
+    if (g.max_row_deg > 128) { set_error("STREAM engine supports check degree <= 128 (got %d)", g.max_row_deg); return LDPC_B200_EUNSUPPORTED; }
+    int fb = (F + TPB - 1) / TPB;
+    int skip = early_exit ? 1 : 0;
+
+    LDPC_CUDA(cudaMemsetAsync(s.ne, 0, (size_t)(E > 0 ? E : 1) * Bp * sizeof(T), st));
+    LDPC_CUDA(cudaMemsetAsync(s.state, 0, Bp, st));
+    LDPC_CUDA(cudaMemsetAsync(s.unsat, 0, Bp, st));
+    LDPC_CUDA(cudaMemsetAsync(s.iters, 0, sizeof(int32_t) * Bp, st));
+    {
+        dim3 grid((N + 31) / 32, (Bp + 31) / 32), blk(32, 8);
+        if (llr_is_double) k_load<T, double><<<grid, blk, 0, st>>>((const double *)d_llr, (T *)s.L, (T *)s.lam, N, F, Bp);
+        else k_load<T, float><<<grid, blk, 0, st>>>((const float *)d_llr, (T *)s.L, (T *)s.lam, N, F, Bp);
+        d->launches++;
+    }
+    std::vector<T> tmp;
+    for (int n = 0;; n++) {
+        if (M > 0) { k_syndrome<T><<<dim3(fb, M), TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
+        LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));
+        k_status<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.unsat, s.iters, s.active, n, max_iters, F);
+        k_hard<T><<<dim3(fb, words_per_frame(N)), TPB, 0, st>>>((const T *)s.lam, (const T *)s.L, s.state, s.iters, d_bits, n, N, F, Bp);
+        d->launches += 2;
+        if (n >= max_iters) break;
+        if (early_exit) {
+            int active = 0;
+            LDPC_CUDA(cudaMemcpyAsync(&active, s.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LDPC_CUDA(cudaStreamSynchronize(st));
+            if (active == 0) break;
+        }
+        dim3 gcn(fb, M);
+        if (d->algo == LDPC_B200_ALGO_SPA) launch_cn<T, LDPC_B200_ALGO_SPA>(d, gcn, F, skip);
+        else launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, gcn, F, skip);
+        k_vn<T><<<dim3(fb, N), TPB, 0, st>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, Bp, skip);
+        d->launches++;
+        if (h_c2v || h_lam) {   // trace of frame 0: column 0 of the frame-minor arrays
+            size_t need = (size_t)(E > N ? E : N);
+            tmp.resize(need);
+            LDPC_CUDA(cudaStreamSynchronize(st));
+            if (h_c2v && E > 0) {
+                LDPC_CUDA(cudaMemcpy2D(tmp.data(), sizeof(T), s.ne, (size_t)Bp * sizeof(T), sizeof(T), E, cudaMemcpyDeviceToHost));
+                for (int e = 0; e < E; e++) h_c2v[(size_t)n * E + e] = (double)tmp[e];
+            }
+            if (h_lam) {
+                LDPC_CUDA(cudaMemcpy2D(tmp.data(), sizeof(T), s.lam, (size_t)Bp * sizeof(T), sizeof(T), N, cudaMemcpyDeviceToHost));
+                for (int j = 0; j < N; j++) h_lam[(size_t)n * N + j] = (double)tmp[j];
+            }
+        }
+    }
+    k_finish<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.iters, d_iters, d_conv, F);
+    d->launches++;
+    LDPC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int stream_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                  bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv,
+                  double *h_trace_c2v, double *h_trace_lam)
+{
+    int rc = stream_alloc(d);
+    if (rc) return rc;
+    if (n_frames > d->sb.Bp) { set_error("n_frames %d exceeds decoder max_batch", n_frames); return LDPC_B200_EINVAL; }
+    if (d->precision == LDPC_B200_PREC_FP64)
+        return stream_decode_t<double>(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits_packed, d_iters, d_conv, h_trace_c2v, h_trace_lam);
+    return stream_decode_t<float>(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits_packed, d_iters, d_conv, h_trace_c2v, h_trace_lam);
+}
+
+}  // namespace ldpc

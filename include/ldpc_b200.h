@@ -1,0 +1,155 @@
+/*
+ * ldpc_b200.h -- C ABI of libldpc_b200.so, the B200 (sm_100a) replacement for the decode path of
+ * ku-fpg/ecc-ldpc.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   ldpc_b200_init / _shutdown        the `initialize` / `finalize` pair a Code carries
+ *                                     (src/ECC/Code/LDPC/Utils.hs:91-103; precedent
+ *                                     src/ECC/Code/LDPC/GPU/CUDA/Arraylet2.hs:287-297)
+ *   ldpc_b200_code_create_csr         `loadMatrix` result as `Matrix Bool` (Utils.hs:40,
+ *                                     src/Data/BitMatrix/Loader.hs:34-39) handed to `decoder0 h`
+ *   ldpc_b200_code_create_qc          `QuasiCyclic Integer` H (Loader.hs:41-46) in the circulant-offset
+ *                                     form of Arraylet2.hs:325-331 (-1 = zero block)
+ *   ldpc_b200_decoder_create          one `decoder0 h` call (Utils.hs:53): per-thread decoder state
+ *   ldpc_b200_decode                  the `decoder` slot of mkLDPC_CodeIO (Utils.hs:95):
+ *                                     Rate -> Int -> U.Vector Double -> IO (Maybe (U.Vector Bool)),
+ *                                     batched over n_frames; algorithm of Reference/Orig.hs:58-98 (SPA)
+ *                                     and Reference/Min.hs:54-104 (min-sum, alpha = 3/4)
+ *   ldpc_b200_decode_trace            per-iteration `ne'` / `lam'` of Orig.hs:81-98 for message-level checks
+ *   ldpc_b200_decode_device           same decode with buffers already resident in HBM
+ *   ldpc_b200_simulate*               what ECC.Tester (ecc-manifold, external) does around `decode`:
+ *                                     BPSK + AWGN frames, decode, count bit / frame errors
+ *   ldpc_b200_ecc_*                   the ECC record built by mkLDPC (Utils.hs:35-75): name grammar,
+ *                                     unpuncture, encode, decode, message_length, codeword_length
+ *
+ * Conventions (Utils.hs / Orig.hs): LLR > 0 decides bit 1; ties decide 0; the syndrome is tested before
+ * every iteration including iteration 0; a frame that is still unsatisfied after max_iters iterations
+ * returns the hard decision of its ORIGINAL channel LLRs (Orig.hs:68-71).
+ * All functions return 0 on success and a negative LDPC_B200_E* code on failure; nothing throws or
+ * aborts across this boundary.  There is no CPU fallback: without a CUDA device every call that needs
+ * one fails with LDPC_B200_ENODEV.
+ */
+#ifndef LDPC_B200_H
+#define LDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDPC_B200_ABI_VERSION 1
+
+enum {
+    LDPC_B200_OK = 0,
+    LDPC_B200_EINVAL = -1,    /* bad argument */
+    LDPC_B200_ENODEV = -2,    /* no CUDA device / not initialised */
+    LDPC_B200_ECUDA = -3,     /* CUDA runtime error, see ldpc_b200_last_error() */
+    LDPC_B200_ENOMEM = -4,
+    LDPC_B200_EUNSUPPORTED = -5
+};
+
+enum { LDPC_B200_ALGO_SPA = 0, LDPC_B200_ALGO_MINSUM = 1 };
+enum { LDPC_B200_PREC_FP64 = 0, LDPC_B200_PREC_FP32 = 1 };
+/* STREAM   : any H; messages live in HBM, frame-minor layout, one launch per phase.
+ * RESIDENT : quasi-cyclic H with single-weight circulants; the whole frame state stays in
+ *            registers / shared memory of one CTA for all iterations.
+ * AUTO     : RESIDENT when the code and precision allow it, else STREAM. */
+enum { LDPC_B200_ENGINE_AUTO = 0, LDPC_B200_ENGINE_STREAM = 1, LDPC_B200_ENGINE_RESIDENT = 2 };
+
+typedef struct ldpc_b200_code ldpc_b200_code_t;
+typedef struct ldpc_b200_decoder ldpc_b200_decoder_t;
+
+/* Counters of a simulation run (what the tester accumulates per Eb/N0 point). */
+typedef struct ldpc_b200_counters {
+    uint64_t frames;        /* frames decoded */
+    uint64_t frame_errors;  /* frames with >= 1 wrong message bit */
+    uint64_t bit_errors;    /* wrong bits among the first k_info bits of every frame */
+    uint64_t sum_iters;     /* iterations executed, summed over frames */
+    uint64_t unconverged;   /* frames that fell back to the channel hard decision */
+    double kernel_ms;       /* device time of the decode kernels (CUDA events) */
+} ldpc_b200_counters_t;
+
+int ldpc_b200_abi_version(void);
+const char *ldpc_b200_last_error(void);
+
+/* device = CUDA ordinal, or -1 for the current device. Idempotent. */
+int ldpc_b200_init(int device);
+void ldpc_b200_shutdown(void);
+int ldpc_b200_device_count(void);
+
+/* H as CSR: check m has variables col_idx[row_ptr[m] .. row_ptr[m+1]) in ascending order. Arrays are copied. */
+int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_t *col_idx, ldpc_b200_code_t **out);
+/* H as brows x bcols circulants of size sz: shifts[r*bcols+c] = k means ones at (r*sz+i, c*sz+(i+k)%sz); -1 = zero. */
+int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts, ldpc_b200_code_t **out);
+void ldpc_b200_code_destroy(ldpc_b200_code_t *code);
+int ldpc_b200_code_info(const ldpc_b200_code_t *code, int *M, int *N, int *E, int *qc_sz);
+
+/* One decoder per host thread: owns a stream and its device buffers, so no locking is needed. */
+int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precision, int max_batch,
+                             ldpc_b200_decoder_t **out);
+int ldpc_b200_decoder_set_engine(ldpc_b200_decoder_t *dec, int engine);
+int ldpc_b200_decoder_engine(const ldpc_b200_decoder_t *dec);   /* engine a decode call will use */
+void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *dec);
+
+/* Host-buffer decode. llr: n_frames x N float64 (zeros at punctured positions); bits: n_frames x N, 0/1;
+ * iters / converged (n_frames each) may be NULL. Synchronous. n_frames may exceed max_batch. */
+int ldpc_b200_decode(ldpc_b200_decoder_t *dec, int max_iters, int n_frames, const double *llr,
+                     uint8_t *bits, int32_t *iters, uint8_t *converged);
+/* Same with float32 LLRs in and bit-packed decisions out (bit j of frame f = word f*ceil(N/32)+j/32, bit j%32). */
+int ldpc_b200_decode_f32(ldpc_b200_decoder_t *dec, int max_iters, int n_frames, const float *llr,
+                         uint32_t *bits_packed, int32_t *iters, uint8_t *converged);
+
+/* One frame, with the messages of every executed iteration t (0-based): c2v[t*E + e] = ne'[edge e] in
+ * reference edge order (row-major, ascending column), lam[t*N + j] = lam'[j]. Arrays hold max_iters rows.
+ * Always runs the STREAM engine (its operation order is the reference's). */
+int ldpc_b200_decode_trace(ldpc_b200_decoder_t *dec, int max_iters, const double *llr, double *c2v,
+                           double *lam, int32_t *iters, uint8_t *bits, uint8_t *converged);
+
+/* Device-resident decode: d_llr is n_frames x N in the decoder's precision (float for FP32, double for
+ * FP64), d_bits_packed is n_frames x ceil(N/32) uint32, d_iters / d_converged may be NULL.
+ * early_exit = 0 executes exactly max_iters iterations for every frame (the convergence test still
+ * selects the output, so decisions equal the early-exit run's). n_frames <= max_batch. Asynchronous
+ * on the decoder's stream; ldpc_b200_decoder_sync waits for it. */
+int ldpc_b200_decode_device(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, int n_frames,
+                            const void *d_llr, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_converged);
+int ldpc_b200_decoder_sync(ldpc_b200_decoder_t *dec);
+/* Device time (ms) of the decode kernels of the last decode* call on this decoder, and launches it made. */
+int ldpc_b200_decoder_last_timing(ldpc_b200_decoder_t *dec, double *kernel_ms, int64_t *launches);
+
+/* Channel frames on the device: BPSK (bit b -> 2b-1) + AWGN, sigma^2 = 1/(2 R 10^(ebn0/10)), R = k_info/n_tx,
+ * LLR = 2y/sigma^2 for the first n_tx positions and 0 for the punctured rest (Utils.hs:55). Noise is
+ * Philox4x32-10 keyed by seed with the global frame index as the stream id, so results do not depend on
+ * batching or on the number of GPUs. d_codewords: NULL = all-zero codeword, else n_frames x ceil(N/32) packed.
+ * d_llr: n_frames x N in the decoder's precision. */
+int ldpc_b200_generate_llr(ldpc_b200_decoder_t *dec, double ebn0_db, int k_info, int n_tx, uint64_t seed,
+                           uint64_t first_frame, int n_frames, const uint32_t *d_codewords, void *d_llr);
+
+/* Generate + decode + count on the device for frames [first_frame, first_frame + n_frames).
+ * Counters are ADDED to *out. all-zero codeword. */
+int ldpc_b200_simulate(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, double ebn0_db, int k_info,
+                       int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames, ldpc_b200_counters_t *out);
+/* Same, but the five integer counters are accumulated into d_counters (5 x uint64 in device memory, e.g. the
+ * send buffer of an all-reduce) on the decoder's stream, with no host synchronisation. */
+int ldpc_b200_simulate_device(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, double ebn0_db, int k_info,
+                              int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames, uint64_t *d_counters);
+
+/* Raw device memory helpers so a host without a CUDA binding (Haskell, ctypes) can stage buffers. */
+int ldpc_b200_malloc(void **d_ptr, uint64_t bytes);
+int ldpc_b200_free(void *d_ptr);
+int ldpc_b200_malloc_host(void **h_ptr, uint64_t bytes);   /* pinned */
+int ldpc_b200_free_host(void *h_ptr);
+int ldpc_b200_memcpy_h2d(void *d_dst, const void *h_src, uint64_t bytes);
+int ldpc_b200_memcpy_d2h(void *h_dst, const void *d_src, uint64_t bytes);
+int ldpc_b200_memset(void *d_ptr, int value, uint64_t bytes);
+/* CUDA stream handle (cudaStream_t) of a decoder, for callers that do share a CUDA runtime. */
+void *ldpc_b200_decoder_stream(ldpc_b200_decoder_t *dec);
+
+/* Philox4x32-10 block function, exported for known-answer tests. */
+int ldpc_b200_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H */

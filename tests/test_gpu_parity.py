@@ -1,0 +1,192 @@
+"""GPU parity suite (run with -m gpu on the B200 box): every test goes through the C ABI of
+libldpc_b200.so and compares with the CPU oracle / the committed golden fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, awgn_llrs, golden
+
+pytestmark = pytest.mark.gpu
+
+CODES = ["moon.7.13", "jpl.1024.4.5", "jpl.4096.4.5", "1920.1280.3.303"]
+TX = {"moon.7.13": None, "jpl.1024.4.5": 1280, "jpl.4096.4.5": 5120, "1920.1280.3.303": None}
+EBN0 = {"moon.7.13": 3.0, "jpl.1024.4.5": 3.7, "jpl.4096.4.5": 3.6, "1920.1280.3.303": 2.4}
+
+
+def _golden_files():
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def _parse(fname):
+    code, algo, it = fname[:-4].rsplit("_", 2)
+    return code, algo, int(it[2:])
+
+
+@pytest.fixture(scope="module")
+def dcodes(gpu_lib, builtin_codes):
+    return {n: gpu_lib.DeviceCode(c) for n, c in builtin_codes.items()}
+
+
+def spa_close(a, b):
+    """Message-level comparison for sum-product in fp64. Min-sum is exact; SPA goes through tanh/atanh of two
+    different libms, and atanh amplifies a 1-ulp difference of the product p by 1/(1-p^2),
+    so: 1e-9 relative where |msg| <= 12, and 1e-12 absolute in the tanh domain everywhere."""
+    a, b = np.asarray(a), np.asarray(b)
+    small = np.abs(b) <= 12.0
+    ok_small = np.all(np.abs(a - b)[small] <= 1e-9 * np.maximum(np.abs(b[small]), 1e-300) + 1e-300)
+    ok_tanh = np.all(np.abs(np.tanh(a / 2) - np.tanh(b / 2)) <= 1e-12)
+    return ok_small and ok_tanh
+
+
+@pytest.mark.parametrize("fname", _golden_files())
+def test_fp64_stream_matches_golden(fname, gpu_lib, dcodes):
+    code_name, algo, max_iters = _parse(fname)
+    g = golden(fname)
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp64", max_batch=8, engine=gpu_lib.ENGINE_STREAM)
+    bits, iters, conv = dec.decode(g["llr"], max_iters)
+    assert np.array_equal(iters, g["iters"])
+    assert np.array_equal(conv, g["converged"])
+    assert np.array_equal(bits, g["bits"])
+    for f in range(g["llr"].shape[0]):
+        b, it, cv, c2v, lam = dec.decode_trace(g["llr"][f], max_iters)
+        assert it == g["iters"][f] and cv == bool(g["converged"][f]) and np.array_equal(b, g["bits"][f])
+        if it == 0:
+            continue
+        if algo == "min":      # bit-exact messages
+            assert np.array_equal(c2v[0], g["c2v_first"][f]) and np.array_equal(c2v[-1], g["c2v_last"][f])
+            assert np.array_equal(lam[0], g["lam_first"][f]) and np.array_equal(lam[-1], g["lam_last"][f])
+            if "c2v_all" in g.files:
+                assert np.array_equal(c2v, g["c2v_all"][f][:it]) and np.array_equal(lam, g["lam_all"][f][:it])
+        else:
+            assert spa_close(c2v[0], g["c2v_first"][f]) and spa_close(c2v[-1], g["c2v_last"][f])
+            assert spa_close(lam[0], g["lam_first"][f]) and spa_close(lam[-1], g["lam_last"][f])
+    dec.close()
+
+
+@pytest.mark.parametrize("code_name", CODES)
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_fp64_stream_matches_oracle_batch(code_name, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    code = builtin_codes[code_name]
+    F = 700 if code_name == "moon.7.13" else 160
+    llr = awgn_llrs(code, EBN0[code_name], F, 1001, TX[code_name])
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp64", max_batch=256, engine=gpu_lib.ENGINE_STREAM)   # F > max_batch: chunking
+    bits, iters, conv = dec.decode(llr, 20)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=0)
+    same = (bits == rb).all(axis=1)
+    if algo == "min":
+        assert same.all() and np.array_equal(iters, ri) and np.array_equal(conv, rc)
+    else:
+        assert same.mean() >= 0.999 and (iters == ri).mean() >= 0.99
+    dec.close()
+
+
+@pytest.mark.parametrize("code_name", CODES)
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_fp32_stream_decisions_vs_oracle(code_name, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """Production precision: hard decisions identical on >= 99.9 % of frames (BASELINE.json north_star)."""
+    code = builtin_codes[code_name]
+    F = 4096 if code_name == "moon.7.13" else (1024 if algo == "min" else 256)
+    llr = awgn_llrs(code, EBN0[code_name] + 0.3, F, 2002, TX[code_name])
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=1024, engine=gpu_lib.ENGINE_STREAM)
+    bits, iters, conv = dec.decode(llr, 20)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=1 if algo == "min" else 0)
+    same = (bits == rb).all(axis=1)
+    assert same.mean() >= 0.999, (same.mean(), F)
+    dec.close()
+
+
+def test_fp32_trace_within_1e4(gpu_lib, dcodes, builtin_codes, oracles):
+    """fp32 production messages within 1e-4 relative of the fp64 oracle (min-sum, first iterations)."""
+    code = builtin_codes["jpl.1024.4.5"]
+    llr = awgn_llrs(code, 3.9, 4, 77, 1280)
+    dec = gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp32", max_batch=4, engine=gpu_lib.ENGINE_STREAM)
+    for f in range(4):
+        llr32 = llr[f].astype(np.float32).astype(np.float64)     # the decoder rounds its input to fp32 first
+        b, it, cv, c2v, lam = dec.decode_trace(llr32, 4)
+        rb, rit, rcv, rc2v, rlam = oracles["jpl.1024.4.5"].decode("min", 4, llr32, trace=True)
+        n = min(it, rit)
+        assert n >= 1
+        scale = np.maximum(np.abs(rc2v[:n]), 1e-3)
+        assert (np.abs(c2v[:n] - rc2v[:n]) / scale).max() <= 1e-4
+        assert (np.abs(lam[:n] - rlam[:n]) / np.maximum(np.abs(rlam[:n]), 1.0)).max() <= 1e-4
+    dec.close()
+
+
+def test_edge_cases(gpu_lib, dcodes, builtin_codes, oracles):
+    code = builtin_codes["jpl.1024.4.5"]
+    dec = gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp64", max_batch=16, engine=gpu_lib.ENGINE_STREAM)
+    # empty batch
+    b, it, cv = dec.decode(np.zeros((0, code.N)), 20)
+    assert b.shape == (0, code.N)
+    # all-zero LLRs: syndrome passes at iteration 0 with the all-zero word (hard(0) = 0)
+    b, it, cv = dec.decode(np.zeros((3, code.N)), 20)
+    assert not b.any() and (it == 0).all() and cv.all()
+    # max_iters = 0 and a hopeless frame: fallback to hard(channel)
+    llr = awgn_llrs(code, -2.0, 5, 5, 1280)
+    for mi in (0, 1, 3):
+        b, it, cv = dec.decode(llr, mi)
+        assert (it == mi).all() and not cv.any()
+        assert np.array_equal(b, (llr > 0).astype(np.uint8))
+    # a valid codeword is a fixed point
+    from oracle import oracle
+    msg = np.random.default_rng(0).integers(0, 2, code.K).astype(np.uint8)
+    cw = oracle.encode(code, msg)
+    b, it, cv = dec.decode((8.0 * (2.0 * cw - 1.0))[None, :], 20)
+    assert it[0] == 0 and cv[0] and np.array_equal(b[0], cw)
+    # ragged: batch of 1 through a decoder sized for 16, and 17 frames (2 chunks)
+    llr = awgn_llrs(code, 3.8, 17, 6, 1280)
+    b1, it1, cv1 = dec.decode(llr[:1], 20)
+    b17, it17, cv17 = dec.decode(llr, 20)
+    rb, ri, rc = oracles["jpl.1024.4.5"].decode_batch("min", 20, llr)
+    assert np.array_equal(b17, rb) and np.array_equal(it17, ri) and np.array_equal(b1[0], rb[0])
+    dec.close()
+
+
+def test_bad_arguments_fail_loudly(gpu_lib, dcodes):
+    import ctypes as C
+    L = gpu_lib.load()
+    h = C.c_void_p()
+    rp = np.array([0, 2], dtype=np.int32)
+    ci = np.array([1, 0], dtype=np.int32)          # not ascending
+    assert L.ldpc_b200_code_create_csr(1, 2, rp.ctypes.data, ci.ctypes.data, C.byref(h)) == -1
+    assert b"ascending" in L.ldpc_b200_last_error()
+    sh = np.array([5], dtype=np.int32)             # shift >= sz
+    assert L.ldpc_b200_code_create_qc(4, 1, 1, sh.ctypes.data, C.byref(h)) == -1
+    assert L.ldpc_b200_decoder_create(dcodes["moon.7.13"].h, 7, 1, 4, C.byref(h)) == -1
+    dec = gpu_lib.Decoder(dcodes["moon.7.13"], "min", "fp32", max_batch=4)
+    with pytest.raises(gpu_lib.LdpcError):
+        dec.set_engine(gpu_lib.ENGINE_RESIDENT)    # general (non-QC) code
+    dec.close()
+
+
+def test_device_generator_statistics_and_simulate(gpu_lib, dcodes, builtin_codes, oracles):
+    """generate_llr: mean / variance / punctured zeros; simulate == generate + decode + count."""
+    code = builtin_codes["jpl.1024.4.5"]
+    K, n_tx, F, ebn0 = code.K, 1280, 512, 3.6
+    dec = gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp32", max_batch=256, engine=gpu_lib.ENGINE_STREAM)
+    buf = gpu_lib.DeviceBuffer(F * code.N * 4)
+    dec.generate_llr(buf.ptr, ebn0, K, n_tx, 42, 1000, F)
+    dec.sync()
+    llr = buf.download(np.float32, (F, code.N)).astype(np.float64)
+    assert not llr[:, n_tx:].any()
+    sigma2 = 1.0 / (2 * (K / n_tx) * 10 ** (ebn0 / 10))
+    y = llr[:, :n_tx] * sigma2 / 2
+    assert abs(y.mean() + 1.0) < 5 * np.sqrt(sigma2 / y.size)
+    assert abs(y.var() / sigma2 - 1.0) < 0.02
+    # frame-index keyed streams: a sub-range regenerates the same frames
+    buf2 = gpu_lib.DeviceBuffer(16 * code.N * 4)
+    dec.generate_llr(buf2.ptr, ebn0, K, n_tx, 42, 1100, 16)
+    dec.sync()
+    assert np.array_equal(buf2.download(np.float32, (16, code.N)), llr[100:116].astype(np.float32))
+    # simulate over the same frames == oracle on the downloaded LLRs
+    c = dec.simulate(20, ebn0, K, n_tx, 42, 1000, F)
+    rb, ri, rc = oracles["jpl.1024.4.5"].decode_batch("min", 20, llr, variant=1)
+    gb, gi, gc = dec.decode(llr, 20)
+    same = (gb == rb).all(axis=1)
+    assert same.mean() >= 0.999
+    assert c["frames"] == F
+    assert c["bit_errors"] == int(gb[:, :K].sum()) and c["frame_errors"] == int(gb[:, :K].any(axis=1).sum())
+    assert c["sum_iters"] == int(gi.sum()) and c["unconverged"] == int((gc == 0).sum())
+    dec.close()
