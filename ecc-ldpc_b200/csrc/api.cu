@@ -295,6 +295,7 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
     cudaStreamSynchronize(d->stream);
     stream_free(d);
     cudaFree(d->d_in); cudaFree(d->d_bits); cudaFree(d->d_iters); cudaFree(d->d_conv); cudaFree(d->d_counters);
+    cudaFree(d->res_work); cudaFree(d->res_conv_buf);
     if (d->h_pinned) cudaFreeHost(d->h_pinned);
     cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
     cudaStreamDestroy(d->stream); cudaStreamDestroy(d->copy_stream);

@@ -72,6 +72,10 @@ struct ldpc_b200_decoder {
     int64_t last_launches = 0;
     int64_t launches = 0;        // running count within a call
     bool timing_pending = false;
+    // RESIDENT engine scratch
+    unsigned int *res_work = nullptr;   // persistent-CTA work counter
+    void *res_conv_buf = nullptr;       // max_batch x N float, when float64 LLRs feed the fp32 kernel
+    size_t res_conv_bytes = 0;
 };
 
 namespace ldpc {

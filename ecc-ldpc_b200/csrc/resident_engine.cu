@@ -1,10 +1,440 @@
-// resident_engine.cu -- placeholder until the on-chip engine lands (next commit).
+// resident_engine.cu -- RESIDENT engine: flooding min-sum for the quasi-cyclic JPL AR4JA codes with the
+// whole frame state on chip for all iterations.
+//
+// Why: the reference's state model moves 3E+3N words per frame and iteration; streamed from
+// HBM that caps a B200 at ~1.06 M frames/s for jpl.4096.4.5 at 20 iterations.  Here a frame costs HBM only
+// its LLRs in and its packed decisions out; the binding resources are the ALU pipe and shared memory.
+//
+// Mapping (SZ = circulant size, one frame = 2*SZ threads):
+//   * thread (h, i): check position i of the block rows of half h (tables in qc_tables.inc; the split gives
+//     both halves 78 of the 156 circulants).  Its check->variable messages ne[] live in REGISTERS for the
+//     whole decode (one register per edge, compile-time indexed after full unrolling).
+//   * posteriors lam[N] and channel LLRs L[N] live in SHARED memory.  Circulant (r,k) with shift s connects
+//     check (r,i) to variable (c, (i+s) mod SZ): a warp reads/writes 32 consecutive words -> conflict-free.
+//   * check phase  (Min.hs:75-89 in the two-minimum form of Model.hs:326-343): x = ne - lam gathered from
+//     smem, running min1/min2 and sign parity, syndrome parity of hard(lam) on the fly (Orig.hs:73-78);
+//     then ne' = -3/4 * sign * (|x| == min1 ? min2 : min1) in place.
+//   * vote: barrier.red.or over the frame's threads = "syndrome all zero?"  (Orig.hs:68-69).
+//   * variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in place
+//     in smem in MAXCD stages: stage q adds, for every block column, the message of its q-th LAST block
+//     row.  Within a stage every address is touched by exactly one thread; a barrier separates stages.
+//     This is exactly the reference's right fold, so the fp64 instance is bit-identical to the oracle.
+//   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs).
+//
+// fp32 is the production instance (2 CTAs/SM); fp64 exists to prove the index logic bit-exactly.
 #include "common.cuh"
+#include "philox.cuh"
+#include <utility>
+
 namespace ldpc {
-int resident_kind_for(const ldpc_b200_code *) { return 0; }
-bool resident_supports(const ldpc_b200_decoder *) { return false; }
-int resident_decode(ldpc_b200_decoder *, int, int, int, const void *, bool, uint32_t *, int32_t *, uint8_t *)
-{ set_error("RESIDENT engine not built"); return LDPC_B200_EUNSUPPORTED; }
-int resident_simulate(ldpc_b200_decoder *, int, int, float, float, int, int, uint64_t, uint64_t, uint64_t, uint64_t *)
-{ set_error("RESIDENT engine not built"); return LDPC_B200_EUNSUPPORTED; }
+
+#include "qc_tables.inc"
+
+template <int... Is, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f)
+{
+    (f(std::integral_constant<int, Is>{}), ...);
 }
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+template <typename T> struct FB;
+template <> struct FB<float> {
+    typedef uint32_t B;
+    static constexpr B SIGN = 0x80000000u;
+    static __device__ __forceinline__ B bits(float x) { return __float_as_uint(x); }
+    static __device__ __forceinline__ float val(B b) { return __uint_as_float(b); }
+    static __device__ __forceinline__ float inf() { return __uint_as_float(0x7f800000u); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+};
+template <> struct FB<double> {
+    typedef unsigned long long B;
+    static constexpr B SIGN = 0x8000000000000000ull;
+    static __device__ __forceinline__ B bits(double x) { return (B)__double_as_longlong(x); }
+    static __device__ __forceinline__ double val(B b) { return __longlong_as_double((long long)b); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+};
+
+// Compile-time layout of the per-thread message registers: the rows of a half, in order, each with row_deg slots.
+template <class C> struct QcMap {
+    static __host__ __device__ constexpr int reg_base(int r)
+    {
+        int h = C::half_of_row[r], b = 0;
+        for (int q = 0; q < C::HR; q++) {
+            int rr = C::half_rows[h][q];
+            if (rr == r) return b;
+            b += C::row_deg[rr];
+        }
+        return -1;
+    }
+    static __host__ __device__ constexpr int half_edges(int h)
+    {
+        int b = 0;
+        for (int q = 0; q < C::HR; q++) b += C::row_deg[C::half_rows[h][q]];
+        return b;
+    }
+    static constexpr int NEH = half_edges(0) > half_edges(1) ? half_edges(0) : half_edges(1);
+    static constexpr int N = C::BC * C::SZ;
+};
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool bar_or(int id, int nthreads, bool pred)
+{
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %3, 0;\n\tbarrier.red.or.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)pred) : "memory");
+    return r != 0;
+}
+
+template <class C>
+__device__ __forceinline__ int var_pos(int i, int s)
+{
+    return (s == 0) ? i : ((i + s) & (C::SZ - 1));
+}
+
+// Check-node phase for the rows of half H. Returns true if any of this thread's checks is unsatisfied by hard(lam).
+template <class C, typename T, int H>
+__device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__restrict__ lam, int i)
+{
+    typedef FB<T> F;
+    bool unsat = false;
+    static_for<C::HR>([&](auto qi) {
+        constexpr int r = C::half_rows[H][decltype(qi)::value];
+        constexpr int d = C::row_deg[r];
+        constexpr int base = QcMap<C>::reg_base(r);
+        T m1 = F::inf(), m2 = F::inf();
+        typename F::B parx = 0;
+        bool par = false;
+        static_for<d>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            constexpr int c = C::row_col[r][k];
+            constexpr int s = C::row_shift[r][k];
+            T l = lam[c * C::SZ + var_pos<C>(i, s)];
+            T x = F::sub(ne[base + k], l);              // -(lam_j - ne[m,j])   (Min.hs:80)
+            ne[base + k] = x;
+            T a = F::abs_(x);
+            m2 = F::min_(m2, F::max_(m1, a));
+            m1 = F::min_(m1, a);
+            parx ^= F::bits(x);
+            par ^= (l > (T)0);                          // hard = (> 0)
+        });
+        unsat |= par;
+        // (-3/4) * (product of the other signs) * (min of the other magnitudes)   (Min.hs:79,89)
+        typename F::B sp = parx & F::SIGN;
+        typename F::B A = F::bits(F::mul((T)-0.75, m1)) ^ sp;
+        typename F::B Bm = F::bits(F::mul((T)-0.75, m2)) ^ sp;
+        static_for<d>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            T x = ne[base + k];
+            typename F::B sel = (F::abs_(x) == m1) ? Bm : A;   // ties: min2 == min1, either is right
+            ne[base + k] = F::val(sel ^ (F::bits(x) & F::SIGN));
+        });
+    });
+    return unsat;
+}
+
+// Syndrome only (used for the test after the last iteration).
+template <class C, typename T, int H>
+__device__ __forceinline__ bool synd_phase(const T *__restrict__ lam, int i)
+{
+    bool unsat = false;
+    static_for<C::HR>([&](auto qi) {
+        constexpr int r = C::half_rows[H][decltype(qi)::value];
+        constexpr int d = C::row_deg[r];
+        bool par = false;
+        static_for<d>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            constexpr int c = C::row_col[r][k];
+            constexpr int s = C::row_shift[r][k];
+            par ^= (lam[c * C::SZ + var_pos<C>(i, s)] > (T)0);
+        });
+        unsat |= par;
+    });
+    return unsat;
+}
+
+// Variable-node stage Q for half H: every block column adds the message of its Q-th last block row.
+template <class C, typename T, int H, int Q>
+__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], T *__restrict__ lam, const T *__restrict__ L, int i)
+{
+    typedef FB<T> F;
+    static_for<C::BC>([&](auto ci) {
+        constexpr int c = decltype(ci)::value;
+        if constexpr (Q < C::col_deg[c]) {
+            constexpr int r = C::col_row_desc[c][Q];
+            if constexpr (C::half_of_row[r] == H) {
+                constexpr int k = C::col_k_desc[c][Q];
+                constexpr int s = C::row_shift[r][k];
+                constexpr int e = QcMap<C>::reg_base(r) + k;
+                int idx = c * C::SZ + var_pos<C>(i, s);
+                T acc = (Q == 0) ? L[idx] : lam[idx];
+                lam[idx] = F::add(ne[e], acc);
+            }
+        }
+    });
+}
+
+struct ResidentParams {
+    const void *llr;               // [F][N] in T, or nullptr: generate on the fly (simulate)
+    uint32_t *bits;                // [F][N/32] or nullptr
+    int32_t *iters;                // [F] or nullptr
+    uint8_t *conv;                 // [F] or nullptr
+    unsigned long long *counters;  // 5 x u64 or nullptr
+    unsigned int *work;            // work counter (zeroed before launch)
+    unsigned int n_frames;
+    int max_iters, early_exit;
+    // simulate
+    float sigma, scale;
+    int n_tx, k_info;
+    unsigned long long seed, first_frame;
+};
+
+template <class C, typename T, int FPC>
+__global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_resident(ResidentParams p)
+{
+    typedef QcMap<C> Mp;
+    constexpr int N = Mp::N, SZ = C::SZ, TPF = 2 * SZ, WPF = TPF / 32, W = N / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF;
+    const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31, wif = tf >> 5;
+    const int bar = slot + 1;
+    T *lam = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;
+    T *L = lam + N;
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N);
+
+    unsigned long long c_frames = 0, c_ferr = 0, c_berr = 0, c_iters = 0, c_unconv = 0;
+
+    for (;;) {
+        if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
+        bar_sync(bar, TPF);
+        const unsigned int f = s_next[slot];
+        if (f >= p.n_frames) break;
+
+        // ---- frame in: channel LLRs -> L, lam ; messages = 0 (Orig.hs:64-65) ----
+        if (p.llr) {
+            const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
+            for (int j = tf; j < N; j += TPF) { T v = src[j]; L[j] = v; lam[j] = v; }
+        } else {
+            for (int g = tf; g < N / 4; g += TPF) {
+                float nz[4];
+                awgn4(p.seed, p.first_frame + f, (uint32_t)g, nz);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int j = 4 * g + q;
+                    T v = (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0;
+                    L[j] = v; lam[j] = v;
+                }
+            }
+        }
+        T ne[Mp::NEH];
+#pragma unroll
+        for (int e = 0; e < Mp::NEH; e++) ne[e] = (T)0;
+        bar_sync(bar, TPF);
+
+        bool done = false;
+        for (int n = 0;; n++) {
+            bool finished_now = false, conv = false;
+            if (!(done && n == p.max_iters)) {
+                bool unsat;
+                if (n == p.max_iters) unsat = (h == 0) ? synd_phase<C, T, 0>(lam, i) : synd_phase<C, T, 1>(lam, i);
+                else unsat = (h == 0) ? cn_phase<C, T, 0>(ne, lam, i) : cn_phase<C, T, 1>(ne, lam, i);
+                bool any = bar_or(bar, TPF, unsat);
+                if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
+            }
+            if (finished_now) {
+                // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
+                done = true;
+                const T *src = conv ? lam : L;
+                unsigned int errs = 0;
+                for (int w = wif; w < W; w += WPF) {
+                    unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] > (T)0);
+                    if (lane == 0) {
+                        if (p.bits) p.bits[(size_t)f * W + w] = word;
+                        int lo = 32 * w;
+                        if (lo + 32 <= p.k_info) errs += __popc(word);
+                        else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
+                    }
+                }
+                if (tf == 0) {
+                    if (p.iters) p.iters[f] = n;
+                    if (p.conv) p.conv[f] = conv ? 1 : 0;
+                }
+                if (p.counters) {
+                    bool anyerr = bar_or(bar, TPF, errs != 0);
+                    c_berr += errs;
+                    if (tf == 0) { c_frames++; c_ferr += anyerr; c_iters += n; c_unconv += !conv; }
+                } else if (!p.early_exit) {
+                    bar_sync(bar, TPF);          // snapshot reads of lam before the next stage-0 writes
+                }
+            }
+            if (n == p.max_iters || (done && p.early_exit)) break;
+
+            // ---- variable phase: lam' = L + sum ne', right fold (Orig.hs:95-98) ----
+            static_for<C::MAXCD>([&](auto qi) {
+                constexpr int Q = decltype(qi)::value;
+                if (h == 0) vn_stage<C, T, 0, Q>(ne, lam, L, i); else vn_stage<C, T, 1, Q>(ne, lam, L, i);
+                bar_sync(bar, TPF);
+            });
+        }
+        // all smem reads of this frame are done before the next frame's loads: the bar_sync after s_next does it
+    }
+
+    if (p.counters) {
+        if (lane == 0 && c_berr) atomicAdd(&p.counters[2], c_berr);
+        if (tf == 0 && c_frames) {
+            atomicAdd(&p.counters[0], c_frames); atomicAdd(&p.counters[1], c_ferr);
+            atomicAdd(&p.counters[3], c_iters); atomicAdd(&p.counters[4], c_unconv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+template <class C>
+static bool matches(const ldpc_b200_code *c)
+{
+    if (c->sz != C::SZ || c->brows != C::BR || c->bcols != C::BC) return false;
+    for (int r = 0; r < C::BR; r++) {
+        int k = 0;
+        for (int b = 0; b < C::BC; b++) {
+            int s = c->shifts[r * C::BC + b];
+            if (s < 0) continue;
+            if (k >= C::row_deg[r] || C::row_col[r][k] != b || C::row_shift[r][k] != s) return false;
+            k++;
+        }
+        if (k != C::row_deg[r]) return false;
+    }
+    return true;
+}
+
+int resident_kind_for(const ldpc_b200_code *c)
+{
+    if (c->sz == 0) return 0;
+    if (matches<QcJpl1024>(c)) return 1;
+    if (matches<QcJpl4096>(c)) return 2;
+    return 0;
+}
+
+bool resident_supports(const ldpc_b200_decoder *d)
+{
+    return d->code->resident_kind != 0 && d->algo == LDPC_B200_ALGO_MINSUM;
+}
+
+template <typename T>
+__global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out, size_t n)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) out[idx] = (T)in[idx];
+}
+
+template <class C, typename T, int FPC>
+static int launch(ldpc_b200_decoder *d, ResidentParams &p)
+{
+    typedef QcMap<C> Mp;
+    auto kern = k_resident<C, T, FPC>;
+    size_t smem = (size_t)FPC * 2 * Mp::N * sizeof(T) + FPC * sizeof(unsigned int);
+    static thread_local int blocks_per_sm = 0;
+    static thread_local int n_sm = 0;
+    if (!blocks_per_sm) {
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FPC * 2 * C::SZ, smem));
+        LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->code->device));
+        if (blocks_per_sm < 1) { set_error("RESIDENT kernel does not fit on this device"); blocks_per_sm = 0; return LDPC_B200_EUNSUPPORTED; }
+    }
+    if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
+    LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), d->stream));
+    p.work = d->res_work;
+    unsigned int groups = (p.n_frames + FPC - 1) / FPC;
+    unsigned int grid = std::min<unsigned int>(groups, (unsigned int)(blocks_per_sm * n_sm));
+    if (grid == 0) return 0;
+    kern<<<grid, FPC * 2 * C::SZ, smem, d->stream>>>(p);
+    d->launches++;
+    LDPC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int launch_kind(ldpc_b200_decoder *d, ResidentParams &p)
+{
+    switch (d->code->resident_kind) {
+    case 1: return launch<QcJpl1024, T, 4>(d, p);
+    case 2: return launch<QcJpl4096, T, 1>(d, p);
+    default: set_error("no RESIDENT specialisation for this code"); return LDPC_B200_EUNSUPPORTED;
+    }
+}
+
+static int launch_prec(ldpc_b200_decoder *d, ResidentParams &p)
+{
+    return d->precision == LDPC_B200_PREC_FP64 ? launch_kind<double>(d, p) : launch_kind<float>(d, p);
+}
+
+int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
+                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv)
+{
+    if (!resident_supports(d)) { set_error("RESIDENT engine does not support this decoder"); return LDPC_B200_EUNSUPPORTED; }
+    int N = d->code->N;
+    const void *src = d_llr;
+    if (llr_is_double && d->precision == LDPC_B200_PREC_FP32) {
+        size_t need = (size_t)d->max_batch * N * sizeof(float);
+        if (d->res_conv_bytes < need) {
+            if (d->res_conv_buf) cudaFree(d->res_conv_buf);
+            d->res_conv_buf = nullptr; d->res_conv_bytes = 0;
+            LDPC_CUDA(cudaMalloc(&d->res_conv_buf, need));
+            d->res_conv_bytes = need;
+        }
+        size_t n = (size_t)n_frames * N;
+        k_convert_f64<float><<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>((const double *)d_llr, (float *)d->res_conv_buf, n);
+        d->launches++;
+        src = d->res_conv_buf;
+    } else if (!llr_is_double && d->precision == LDPC_B200_PREC_FP64) {
+        set_error("fp64 decoder needs float64 LLRs");
+        return LDPC_B200_EINVAL;
+    }
+    ResidentParams p = {};
+    p.llr = src; p.bits = d_bits_packed; p.iters = d_iters; p.conv = d_conv; p.counters = nullptr;
+    p.n_frames = (unsigned int)n_frames; p.max_iters = max_iters; p.early_exit = early_exit;
+    p.k_info = 0; p.n_tx = N;
+    return launch_prec(d, p);
+}
+
+int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float sigma, float llr_scale,
+                      int k_info, int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
+                      uint64_t *d_counters)
+{
+    if (!resident_supports(d)) { set_error("RESIDENT engine does not support this decoder"); return LDPC_B200_EUNSUPPORTED; }
+    const uint64_t chunk = 1ull << 30;
+    for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        ResidentParams p = {};
+        p.llr = nullptr; p.bits = nullptr; p.iters = nullptr; p.conv = nullptr;
+        p.counters = (unsigned long long *)d_counters;
+        p.n_frames = (unsigned int)std::min<uint64_t>(chunk, n_frames - f0);
+        p.max_iters = max_iters; p.early_exit = early_exit;
+        p.sigma = sigma; p.scale = llr_scale; p.n_tx = n_tx; p.k_info = k_info;
+        p.seed = seed; p.first_frame = first_frame + f0;
+        int rc = launch_prec(d, p);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace ldpc
