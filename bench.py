@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path: jpl.4096.4.5 normalised min-sum, 20 iterations.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU restatement of the reference on the host cores)
+
+One "step" = one pass of the decoder over one batch of B frames per GPU whose LLRs are already resident
+in HBM (float32, generated on the device before the timed region).  The workload is the WORST CASE of the
+metric: Eb/N0 = 2.0 dB, where no frame of this code converges, so the reference algorithm itself (syndrome
+test before every iteration, Orig.hs:68-70) executes all 20 iterations on every frame -- nothing is skipped
+and `avg_iters` in the JSON line proves it.  Early-exit operating points are reported under "extra".
+
+value      decoded info Gbit/s = frames * K_info / time, whole job (all ranks), device-timed (CUDA events on the
+           decoder's stream, barrier + synchronize on both sides, max over ranks)
+e2e        same metric through ldpc_b200_decode with HOST float64 LLRs (pinned) in and host decisions out
+roofline   HBM roofline of the decode kernel with the reference's algorithmic bytes (3E+3N words per frame
+           and iteration); the RESIDENT engine keeps that state on chip, so frac may exceed 1
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODE = "jpl.4096.4.5"
+MAX_ITERS = 20
+N_TX = 5120
+EBN0_WORST = 2.0
+SEED = 20261018
+METRIC = "decoded_info_gbit_per_s"
+UNIT = "Gbit/s"
+
+
+def alg_bytes_per_frame(code, iters, w=4):
+    """B_alg = iters * w * (3E + 3N) + w * N_tx + K/8."""
+    return iters * w * (3 * code.E + 3 * code.N) + w * N_TX + code.K // 8
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_arm(args):
+    """CPU arm: the C restatement of the reference decoder (oracle/, kind 'port' -- the Haskell reference cannot be
+    built in this image) on all host cores, same code / algorithm / iteration cap / Eb/N0 as the GPU arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from ecc_ldpc_b200 import codes
+    from oracle import oracle
+    code = codes.load_builtin(CODE)
+    orc = oracle.Oracle(code)
+    cores = oracle.lib().oracle_max_threads()
+    frames = args.cpu_frames or 64 * cores
+    rng = np.random.default_rng(SEED)
+    sigma = np.sqrt(1.0 / (2 * (code.K / N_TX) * 10 ** (EBN0_WORST / 10)))
+    llr = 2.0 * (-1.0 + sigma * rng.standard_normal((frames, code.N))) / sigma ** 2
+    llr[:, N_TX:] = 0.0
+    for _ in range(args.warmup):
+        orc.decode_batch("min", MAX_ITERS, llr[: max(cores, 8)], variant=1, threads=cores)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        bits, iters, conv = orc.decode_batch("min", MAX_ITERS, llr, variant=1, threads=cores)
+        its += int(iters.sum())
+    dt = time.perf_counter() - t0
+    fps = frames * args.steps / dt
+    val = fps * code.K / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
+                   "frames_per_step": frames, "avg_iters": its / (frames * args.steps)},
+        "edge_updates_per_s": fps * (its / (frames * args.steps)) * code.E,
+        "frames_per_s": fps,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d frames x %d steps, two-minimum O(E) check update, one frame per thread" % (frames, args.steps)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=32768, help="frames per step per GPU (LLRs resident in HBM)")
+    ap.add_argument("--e2e-frames", type=int, default=8192, help="frames per step per GPU for the host-buffer e2e leg")
+    ap.add_argument("--cpu-frames", type=int, default=0)
+    ap.add_argument("--engine", default="auto", choices=["auto", "stream", "resident"])
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from ecc_ldpc_b200 import codes, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libldpc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.init(local)
+
+    code = codes.load_builtin(CODE)
+    dcode = lib.DeviceCode(code)
+    B, W = args.frames, code.N // 32
+    engine = {"auto": lib.ENGINE_AUTO, "stream": lib.ENGINE_STREAM, "resident": lib.ENGINE_RESIDENT}[args.engine]
+    dec = lib.Decoder(dcode, "min", "fp32", max_batch=B, engine=engine)
+    ext = torch.cuda.ExternalStream(dec.stream(), device=torch.device("cuda", local))
+
+    # device buffers as torch tensors (torch = memory + streams + NCCL plumbing only)
+    d_llr = torch.empty((B, code.N), dtype=torch.float32, device="cuda")
+    d_bits = torch.zeros((B, W), dtype=torch.int32, device="cuda")
+    d_iters = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_conv = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(5, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def gen(ebn0, first):
+        dec.generate_llr(d_llr.data_ptr(), ebn0, code.K, N_TX, SEED, first, B)
+        dec.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """K steps between barrier+synchronize, CUDA events on the decoder's stream, MAX over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    kernel_ms, launches = [], []
+
+    def step_device(early_exit=True):
+        def fn():
+            dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=early_exit,
+                              d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
+            dec.count_errors(d_cnt.data_ptr(), B, code.K, d_bits.data_ptr(), d_iters.data_ptr(), d_conv.data_ptr())
+            if world > 1:
+                with torch.cuda.stream(ext):      # the path's one exchange step: 5 x u64 error counters over NCCL
+                    dist.all_reduce(d_cnt)
+        return fn
+
+    # ---------------- headline: worst case, all 20 iterations executed ----------------
+    gen(EBN0_WORST, rank * B)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    d_cnt.zero_()
+    total_ms = timed(step_device(True), args.steps, args.warmup)
+    # kernel-only duration of one launch, measured live by the library's own events on the launching stream
+    for _ in range(3):
+        dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=True,
+                          d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
+        dec.sync()
+        ms, nl = dec.last_timing()
+        kernel_ms.append(ms); launches.append(nl)
+    clocks = sampler.stop()
+    avg_iters = float(d_iters.float().mean().item())
+    frames_total = B * world * args.steps
+    fps = frames_total / (total_ms * 1e-3)
+    value = fps * code.K / 1e9
+    k_ms = float(np.median(kernel_ms))
+    b_alg = alg_bytes_per_frame(code, avg_iters)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = B * b_alg / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch_per_frame")
+        if traffic is not None:
+            traffic = traffic * B
+    except Exception:
+        pass
+
+    # ---------------- e2e: host float64 LLRs -> ldpc_b200_decode -> host decisions ----------------
+    Be = args.e2e_frames
+    h_llr = torch.empty((Be, code.N), dtype=torch.float64).pin_memory()
+    h_llr.copy_(d_llr[:Be].double().cpu())
+    h_bits = torch.empty((Be, code.N), dtype=torch.uint8).pin_memory()
+    h_iters = torch.empty(Be, dtype=torch.int32).pin_memory()
+    h_conv = torch.empty(Be, dtype=torch.uint8).pin_memory()
+    L = lib.load()
+
+    def step_e2e():
+        lib.check(L.ldpc_b200_decode(dec.h, MAX_ITERS, Be, h_llr.data_ptr(), h_bits.data_ptr(), h_iters.data_ptr(), h_conv.data_ptr()))
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_fps = Be * world * e2e_steps / float(dt.item())
+    e2e = {"value": e2e_fps * code.K / 1e9, "unit": UNIT, "h2d_bytes_per_step": Be * code.N * 8,
+           "d2h_bytes_per_step": Be * (code.N + 5), "frames_per_step": Be,
+           "api": "ldpc_b200_decode (float64 LLRs, pinned host buffers; uint8 decisions + iters + flags back)"}
+
+    # ---------------- extra operating points with early exit (reference semantics) ----------------
+    extra = {}
+    if not args.no_extra:
+        for ebn0 in (3.5, 4.0, 4.5):
+            gen(ebn0, rank * B)
+            d_cnt.zero_()
+            ms = timed(step_device(True), max(3, args.steps // 2), 1)
+            n = max(3, args.steps // 2)
+            it = float(d_iters.float().mean().item())
+            f = B * world * n / (ms * 1e-3)
+            cnt = d_cnt.clone()
+            extra["ebn0_%.1f" % ebn0] = {"info_gbit_per_s": f * code.K / 1e9, "frames_per_s": f, "avg_iters": it,
+                                          "edge_updates_per_s": f * it * code.E,
+                                          "fer": float((d_conv == 0).float().mean().item())}
+        gen(4.0, rank * B)
+        ms = timed(step_device(False), 3, 1)
+        f = B * world * 3 / (ms * 1e-3)
+        extra["ebn0_4.0_no_early_exit"] = {"info_gbit_per_s": f * code.K / 1e9, "frames_per_s": f, "avg_iters": float(MAX_ITERS),
+                                           "edge_updates_per_s": f * MAX_ITERS * code.E}
+
+    # ---------------- CPU baseline beside it (rank 0, bounded sample) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle
+        orc = oracle.Oracle(code)
+        cores = oracle.lib().oracle_max_threads()
+        gen(EBN0_WORST, 0)
+        nf = args.cpu_frames or 64 * cores
+        sample = d_llr[:nf].double().cpu().numpy()
+        gb = lib.unpack_bits(d_bits[:nf].cpu().numpy().view(np.uint32), code.N) if False else None
+        t0 = time.perf_counter()
+        rb, ri, rc = orc.decode_batch("min", MAX_ITERS, sample, variant=1, threads=cores)
+        dtc = time.perf_counter() - t0
+        dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=True, d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
+        dec.sync()
+        gb = lib.unpack_bits(d_bits[:nf].cpu().numpy().view(np.uint32), code.N)
+        same = float((gb == rb).all(axis=1).mean())
+        cpu = {"value": nf / dtc * code.K / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d frames of the same LLRs (downloaded from the GPU), C restatement oracle/ldpc_oracle.c, two-minimum check update, %d threads, avg %.1f iterations" % (nf, cores, float(ri.mean())),
+               "frames_per_s": nf / dtc, "decisions_identical_to_gpu": same}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
+                       "frames_per_step_per_gpu": B, "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident"}[dec.engine()],
+                       "l2": "inputs larger than L2 (%.0f MB of LLRs per step per GPU)" % (B * code.N * 4 / 1e6),
+                       "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step"},
+            "frames_per_s": fps, "edge_updates_per_s": fps * avg_iters * code.E,
+            "gpu_launches": int(sum(launches) / len(launches) + 1) * args.steps,
+            "clocks": clocks,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel_ms": k_ms, "alg_bytes_per_frame": b_alg,
+                         "note": "algorithmic bytes = reference state model 3E+3N words/frame/iteration (SURVEY.md 8d); peak = MEASURED_PEAKS.json hbm_gbs%s" % ("" if peaks else " (fallback)")},
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -445,7 +445,7 @@ int ldpc_b200_simulate_device(ldpc_b200_decoder_t *d, int max_iters, int early_e
             int F = (int)std::min<uint64_t>((uint64_t)d->max_batch, n_frames - f0);
             rc = channel_generate(d, sigma, scale, n_tx, seed, first_frame + f0, F, nullptr, d->d_in);
             if (!rc) rc = stream_decode(d, max_iters, early_exit, F, d->d_in, d->precision == LDPC_B200_PREC_FP64, d->d_bits, d->d_iters, d->d_conv, nullptr, nullptr);
-            if (!rc) rc = channel_count(d, F, k_info, d->d_bits, d->d_iters, d->d_conv, d_counters);
+            if (!rc) rc = channel_count(d, F, k_info, d->d_bits, nullptr, d->d_iters, d->d_conv, d_counters);
         }
     }
     end_timing(d);
@@ -469,6 +469,14 @@ int ldpc_b200_simulate(ldpc_b200_decoder_t *d, int max_iters, int early_exit, do
     out->frames += h[0]; out->frame_errors += h[1]; out->bit_errors += h[2]; out->sum_iters += h[3]; out->unconverged += h[4];
     out->kernel_ms += d->last_ms;
     return 0;
+}
+
+int ldpc_b200_count_errors(ldpc_b200_decoder_t *d, int n_frames, int k_info, const uint32_t *d_bits_packed,
+                           const uint32_t *d_ref_packed, const int32_t *d_iters, const uint8_t *d_converged, uint64_t *d_counters)
+{
+    if (!d || n_frames < 0 || k_info < 0 || k_info > d->code->N || !d_bits_packed || !d_iters || !d_converged || !d_counters) { set_error("count_errors: bad arguments"); return LDPC_B200_EINVAL; }
+    LDPC_CUDA(cudaSetDevice(d->code->device));
+    return channel_count(d, n_frames, k_info, d_bits_packed, d_ref_packed, d_iters, d_converged, d_counters);
 }
 
 int ldpc_b200_malloc(void **p, uint64_t bytes)

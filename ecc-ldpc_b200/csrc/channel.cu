@@ -46,7 +46,7 @@ int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_t
 }
 
 // counters: [0] frames [1] frame errors [2] bit errors (first k_info bits, all-zero codeword) [3] sum iters [4] unconverged
-__global__ void k_count(const uint32_t *__restrict__ bits, const int32_t *__restrict__ iters,
+__global__ void k_count(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ ref, const int32_t *__restrict__ iters,
                         const uint8_t *__restrict__ conv, int F, int W, int k_info,
                         unsigned long long *__restrict__ counters)
 {
@@ -55,8 +55,8 @@ __global__ void k_count(const uint32_t *__restrict__ bits, const int32_t *__rest
     if (f < F) {
         int full = k_info >> 5, rem = k_info & 31;
         int e = 0;
-        for (int w = 0; w < full; w++) e += __popc(bits[(size_t)f * W + w]);
-        if (rem) e += __popc(bits[(size_t)f * W + full] & ((1u << rem) - 1u));
+        for (int w = 0; w < full; w++) e += __popc(bits[(size_t)f * W + w] ^ (ref ? ref[(size_t)f * W + w] : 0u));
+        if (rem) e += __popc((bits[(size_t)f * W + full] ^ (ref ? ref[(size_t)f * W + full] : 0u)) & ((1u << rem) - 1u));
         be = e; fe = e != 0; it = iters[f]; un = conv[f] == 0; fr = 1;
     }
     for (int o = 16; o; o >>= 1) {
@@ -73,10 +73,10 @@ __global__ void k_count(const uint32_t *__restrict__ bits, const int32_t *__rest
 }
 
 int channel_count(ldpc_b200_decoder *d, int n_frames, int k_info, const uint32_t *d_bits_packed,
-                  const int32_t *d_iters, const uint8_t *d_conv, uint64_t *d_counters)
+                  const uint32_t *d_ref_packed, const int32_t *d_iters, const uint8_t *d_conv, uint64_t *d_counters)
 {
     if (n_frames <= 0) return 0;
-    k_count<<<(n_frames + 127) / 128, 128, 0, d->stream>>>(d_bits_packed, d_iters, d_conv, n_frames,
+    k_count<<<(n_frames + 127) / 128, 128, 0, d->stream>>>(d_bits_packed, d_ref_packed, d_iters, d_conv, n_frames,
                                                            words_per_frame(d->code->N), k_info,
                                                            (unsigned long long *)d_counters);
     d->launches++;

@@ -104,7 +104,7 @@ int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float
 int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_tx, uint64_t seed,
                      uint64_t first_frame, int n_frames, const uint32_t *d_codewords, void *d_llr);
 int channel_count(ldpc_b200_decoder *d, int n_frames, int k_info, const uint32_t *d_bits_packed,
-                  const int32_t *d_iters, const uint8_t *d_conv, uint64_t *d_counters);
+                  const uint32_t *d_ref_packed, const int32_t *d_iters, const uint8_t *d_conv, uint64_t *d_counters);
 int unpack_bits(ldpc_b200_decoder *d, int n_frames, const uint32_t *d_bits_packed, uint8_t *d_bytes);
 
 }  // namespace ldpc

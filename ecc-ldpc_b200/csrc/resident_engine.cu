@@ -18,7 +18,7 @@
 //   * variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in place
 //     in smem in MAXCD stages: stage q adds, for every block column, the message of its q-th LAST block
 //     row.  Within a stage every address is touched by exactly one thread; a barrier separates stages.
-//     This is exactly the reference's right fold, so the fp64 instance is bit-identical to the oracle.
+//     This is exactly the reference's right fold, so the fp64 instance reproduces the reference bit for bit.
 //   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs).
 //
 // fp32 is the production instance (2 CTAs/SM); fp64 exists to prove the index logic bit-exactly.

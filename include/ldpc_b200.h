@@ -135,6 +135,13 @@ int ldpc_b200_simulate(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, 
 int ldpc_b200_simulate_device(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, double ebn0_db, int k_info,
                               int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames, uint64_t *d_counters);
 
+/* Error counting for device-resident decisions: adds {frames, frame errors, bit errors over the first k_info bits,
+ * sum of iterations, unconverged} of n_frames frames to d_counters (5 x uint64, device). d_ref_packed = transmitted
+ * codewords (n_frames x ceil(N/32)) or NULL for the all-zero codeword. Asynchronous on the decoder's stream. */
+int ldpc_b200_count_errors(ldpc_b200_decoder_t *dec, int n_frames, int k_info, const uint32_t *d_bits_packed,
+                           const uint32_t *d_ref_packed, const int32_t *d_iters, const uint8_t *d_converged,
+                           uint64_t *d_counters);
+
 /* Raw device memory helpers so a host without a CUDA binding (Haskell, ctypes) can stage buffers. */
 int ldpc_b200_malloc(void **d_ptr, uint64_t bytes);
 int ldpc_b200_free(void *d_ptr);

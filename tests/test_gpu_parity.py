@@ -205,7 +205,8 @@ def test_resident_fp64_bit_exact_vs_oracle(code_name, gpu_lib, dcodes, builtin_c
     convergence flag are IDENTICAL to the oracle on every frame (min-sum is exact up to the a7 additions)."""
     code = builtin_codes[code_name]
     F = 300
-    llr = awgn_llrs(code, EBN0[code_name], F, 3003, TX[code_name])
+    llr = np.concatenate([awgn_llrs(code, EBN0[code_name], F // 2, 3003, TX[code_name]),
+                          awgn_llrs(code, EBN0[code_name] - 0.7, F // 2, 3004, TX[code_name])])
     dec = gpu_lib.Decoder(dcodes[code_name], "min", "fp64", max_batch=128, engine=gpu_lib.ENGINE_RESIDENT)
     assert dec.engine() == gpu_lib.ENGINE_RESIDENT
     bits, iters, conv = dec.decode(llr, 20)
