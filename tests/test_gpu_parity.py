@@ -318,3 +318,31 @@ def test_resident_simulate_equals_generate_decode_count(code_name, gpu_lib, dcod
     rb, ri, rc = oracles[code_name].decode_batch("min", 20, llr, variant=1)
     assert (gb == rb).all(axis=1).mean() >= 0.998
     dec.close()
+
+
+def test_ecc_record_mirror(gpu_lib, builtin_codes, oracles):
+    """mkLDPC mirror (Utils.hs:35-75): name, lengths, encode, unpuncture + decode + truncate vs the oracle wrapper."""
+    from ecc_ldpc_b200 import ecc
+    from oracle import oracle
+    (e,) = ecc.match("ldpc/b200-minsum/jpl.1024.4.5/20/4/5")
+    code = builtin_codes["jpl.1024.4.5"]
+    assert e.name == "ldpc/b200-minsum/jpl.1024.4.5/20/4/5"
+    assert (e.message_length, e.codeword_length) == (1024, 1280)
+    rng = np.random.default_rng(12)
+    msg = rng.integers(0, 2, 1024).astype(np.uint8)
+    cw = e.encode(msg)
+    assert np.array_equal(cw, oracle.encode(code, msg, 1280))
+    sigma = np.sqrt(1.0 / (2 * 0.8 * 10 ** 0.40))
+    for t in range(6):
+        rx = 2.0 * ((2.0 * cw - 1.0) + sigma * rng.standard_normal(1280)) / sigma ** 2
+        out, flag = e.decode(rx)
+        ref, rflag, it, cv = oracles["jpl.1024.4.5"].ecc_decode("min", 20, 1024, 1280, rx)
+        assert flag and rflag and np.array_equal(out, ref)
+        assert cv and np.array_equal(out, msg)
+    e.close()
+    (e2,) = ecc.match("ldpc/b200-spa-fp64/moon.7.13/20")
+    assert e2.name == "ldpc/b200-spa-fp64/moon.7.13/20/7/20" and e2.codeword_length == 20
+    m = rng.integers(0, 2, 7).astype(np.uint8)
+    out, flag = e2.decode(5.0 * (2.0 * e2.encode(m) - 1.0))
+    assert flag and np.array_equal(out, m)
+    e2.close()

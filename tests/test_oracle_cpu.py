@@ -183,3 +183,14 @@ def test_uncoded_ber_identity(builtin_codes):
     q = 0.5 * erfc(sqrt(2 * (code.K / code.N)) / sqrt(2))
     assert abs(ber - q) < 4 * sqrt(q * (1 - q) / (256 * code.K))
     assert abs(q - 0.11390) < 2e-4
+
+
+def test_code_name_grammar():
+    """Utils.hs:100-108: ldpc/<decoder>/<matrix>/<max-rounds>[/<num>/<den>]; anything else matches nothing."""
+    from ecc_ldpc_b200 import ecc
+    assert ecc.parse_name("ldpc/b200-minsum/jpl.4096.4.5/20/4/5") == ("b200-minsum", "jpl.4096.4.5", 20, (4, 5))
+    assert ecc.parse_name("ldpc/b200-spa/moon.7.13/200") == ("b200-spa", "moon.7.13", 200, None)
+    for bad in ("ldpc/reference/moon.7.13/20", "ldpc/b200-minsum/moon.7.13/x", "ldpc/b200-minsum/moon.7.13",
+                "bpsk", "ldpc/b200-minsum/moon.7.13/20/4", "ldpc/b200-minsum/moon.7.13/20/a/5"):
+        assert ecc.parse_name(bad) is None
+        assert ecc.match(bad) == []
