@@ -26,6 +26,12 @@
 #include "philox.cuh"
 #include <utility>
 
+// Tuning switch: RES_ADDR_IMAD 1 = form the rotated word index (i + s) on the FMA pipe (IMAD with an opaque
+// multiplier 1) instead of the ALU pipe, which is the binding unit of this kernel.
+#ifndef RES_ADDR_IMAD
+#define RES_ADDR_IMAD 0
+#endif
+
 namespace ldpc {
 
 #include "qc_tables.inc"
@@ -54,6 +60,13 @@ template <> struct FB<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    // min' of Min.hs:89 in ONE instruction: FMNMX.XORSIGN = min(|a|,|b|) carrying sign(a) xor sign(b)
+    static __device__ __forceinline__ float box(float a, float b)
+    {
+        float r;
+        asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        return r;
+    }
 };
 template <> struct FB<double> {
     typedef unsigned long long B;
@@ -67,6 +80,10 @@ template <> struct FB<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double box(double a, double b)
+    {
+        return val(bits(fmin(fabs(a), fabs(b))) | ((bits(a) ^ bits(b)) & SIGN));
+    }
 };
 
 // Compile-time layout of the per-thread message registers: the rows of a half, in order, each with row_deg slots.
@@ -104,75 +121,110 @@ __device__ __forceinline__ bool bar_or(int id, int nthreads, bool pred)
 }
 
 template <class C>
-__device__ __forceinline__ int var_pos(int i, int s)
+__device__ __forceinline__ int var_pos(int i, int s, int one)
 {
-    return (s == 0) ? i : ((i + s) & (C::SZ - 1));
+    if (s == 0) return i;
+#if RES_ADDR_IMAD
+    int t;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(i), "r"(one), "r"(s));
+    return t & (C::SZ - 1);
+#else
+    (void)one;
+    return (i + s) & (C::SZ - 1);
+#endif
 }
+
+// Leave-one-out "box" reduction over the D messages of a check row with a binary tree: `build` reduces subtrees
+// bottom-up, `down` hands every leaf the reduction of everything outside it.  The operator is the reference's
+// min' (Min.hs:89: sign product times minimum magnitude), exact in floating point and associative, so the result
+// equals foldr1 min' over the other entries bit for bit.  ~2.7 ops per edge at depth log2(D); the serial
+// min1/min2 recurrence needs a compare+select and two sign operations per edge on top.
+template <typename T, int LO, int HI> struct BoxTree {
+    static constexpr int MID = (LO + HI) / 2;
+    BoxTree<T, LO, MID> l;
+    BoxTree<T, MID, HI> r;
+    T m;
+    template <class A> __device__ __forceinline__ void build(const A &a)
+    {
+        l.build(a); r.build(a);
+        m = FB<T>::box(l.m, r.m);
+    }
+    template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const
+    {
+        l.down(FB<T>::box(o, r.m), emit);
+        r.down(FB<T>::box(o, l.m), emit);
+    }
+    template <class Fn> __device__ __forceinline__ void down_root(Fn &&emit) const
+    {
+        l.down(r.m, emit);
+        r.down(l.m, emit);
+    }
+};
+template <typename T, int LO> struct BoxTree<T, LO, LO + 1> {
+    T m;
+    template <class A> __device__ __forceinline__ void build(const A &a) { m = a(std::integral_constant<int, LO>{}); }
+    template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const { emit(std::integral_constant<int, LO>{}, o); }
+};
+
+// Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
+// round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
+// zero (punctured LLR, or a sum that cancels) is +0.0 in mu, and mu is never -0.0 (x + y = -0 needs both operands
+// -0, and negL = 0 - L is never -0).  Hence hard(lam) = (lam > 0) = sign bit of mu, and the syndrome parity of a
+// check row is the xor of the sign bits of its mu's: half a LOP3 per edge instead of a compare per edge.
 
 // Check-node phase for the rows of half H. Returns true if any of this thread's checks is unsatisfied by hard(lam).
 template <class C, typename T, int H>
-__device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__restrict__ lam, int i)
+__device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__restrict__ mu, int i, int one)
 {
     typedef FB<T> F;
-    bool unsat = false;
+    typename F::B unsat = 0;
     static_for<C::HR>([&](auto qi) {
         constexpr int r = C::half_rows[H][decltype(qi)::value];
         constexpr int d = C::row_deg[r];
         constexpr int base = QcMap<C>::reg_base(r);
-        T m1 = F::inf(), m2 = F::inf();
-        typename F::B parx = 0;
-        bool par = false;
+        typename F::B par = 0;
         static_for<d>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
-            T l = lam[c * C::SZ + var_pos<C>(i, s)];
-            T x = F::sub(ne[base + k], l);              // -(lam_j - ne[m,j])   (Min.hs:80)
-            ne[base + k] = x;
-            T a = F::abs_(x);
-            m2 = F::min_(m2, F::max_(m1, a));
-            m1 = F::min_(m1, a);
-            parx ^= F::bits(x);
-            par ^= (l > (T)0);                          // hard = (> 0)
+            T m = mu[c * C::SZ + var_pos<C>(i, s, one)];
+            par ^= F::bits(m);
+            ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
         });
         unsat |= par;
-        // (-3/4) * (product of the other signs) * (min of the other magnitudes)   (Min.hs:79,89)
-        typename F::B sp = parx & F::SIGN;
-        typename F::B A = F::bits(F::mul((T)-0.75, m1)) ^ sp;
-        typename F::B Bm = F::bits(F::mul((T)-0.75, m2)) ^ sp;
-        static_for<d>([&](auto ki) {
-            constexpr int k = decltype(ki)::value;
-            T x = ne[base + k];
-            typename F::B sel = (F::abs_(x) == m1) ? Bm : A;   // ties: min2 == min1, either is right
-            ne[base + k] = F::val(sel ^ (F::bits(x) & F::SIGN));
-        });
+        // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
+        BoxTree<T, 0, d> tree;
+        tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
+        tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = F::mul((T)-0.75, others); });
     });
-    return unsat;
+    return (unsat & F::SIGN) != 0;
 }
 
 // Syndrome only (used for the test after the last iteration).
 template <class C, typename T, int H>
-__device__ __forceinline__ bool synd_phase(const T *__restrict__ lam, int i)
+__device__ __forceinline__ bool synd_phase(const T *__restrict__ mu, int i, int one)
 {
-    bool unsat = false;
+    typedef FB<T> F;
+    typename F::B unsat = 0;
     static_for<C::HR>([&](auto qi) {
         constexpr int r = C::half_rows[H][decltype(qi)::value];
         constexpr int d = C::row_deg[r];
-        bool par = false;
+        typename F::B par = 0;
         static_for<d>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
-            par ^= (lam[c * C::SZ + var_pos<C>(i, s)] > (T)0);
+            par ^= F::bits(mu[c * C::SZ + var_pos<C>(i, s, one)]);
         });
         unsat |= par;
     });
-    return unsat;
+    return (unsat & F::SIGN) != 0;
 }
 
-// Variable-node stage Q for half H: every block column adds the message of its Q-th last block row.
+// Variable-node stage Q for half H: every block column adds the message of its Q-th last block row (in negated
+// form: mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the exact negation of Orig.hs:95-98).
 template <class C, typename T, int H, int Q>
-__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], T *__restrict__ lam, const T *__restrict__ L, int i)
+__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], T *__restrict__ mu, const T *__restrict__ negL, int i, int one)
 {
     typedef FB<T> F;
     static_for<C::BC>([&](auto ci) {
@@ -183,9 +235,9 @@ __device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], T *__rest
                 constexpr int k = C::col_k_desc[c][Q];
                 constexpr int s = C::row_shift[r][k];
                 constexpr int e = QcMap<C>::reg_base(r) + k;
-                int idx = c * C::SZ + var_pos<C>(i, s);
-                T acc = (Q == 0) ? L[idx] : lam[idx];
-                lam[idx] = F::add(ne[e], acc);
+                int idx = c * C::SZ + var_pos<C>(i, s, one);
+                T acc = (Q == 0) ? negL[idx] : mu[idx];
+                mu[idx] = F::sub(acc, ne[e]);
             }
         }
     });
@@ -204,19 +256,22 @@ struct ResidentParams {
     float sigma, scale;
     int n_tx, k_info;
     unsigned long long seed, first_frame;
+    int c_one;                     // = 1: opaque multiplier for RES_ADDR_IMAD
 };
 
 template <class C, typename T, int FPC>
 __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_resident(ResidentParams p)
 {
     typedef QcMap<C> Mp;
+    typedef FB<T> F;
     constexpr int N = Mp::N, SZ = C::SZ, TPF = 2 * SZ, WPF = TPF / 32, W = N / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF;
     const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31, wif = tf >> 5;
     const int bar = slot + 1;
-    T *lam = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;
-    T *L = lam + N;
+    T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;      // negated posterior, see above
+    T *negL = mu + N;                                                    // negated channel LLRs
+    const int one = p.c_one;
     unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N);
 
     unsigned long long c_frames = 0, c_ferr = 0, c_berr = 0, c_iters = 0, c_unconv = 0;
@@ -230,7 +285,7 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
         // ---- frame in: channel LLRs -> L, lam ; messages = 0 (Orig.hs:64-65) ----
         if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
-            for (int j = tf; j < N; j += TPF) { T v = src[j]; L[j] = v; lam[j] = v; }
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
         } else {
             for (int g = tf; g < N / 4; g += TPF) {
                 float nz[4];
@@ -238,8 +293,8 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     int j = 4 * g + q;
-                    T v = (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0;
-                    L[j] = v; lam[j] = v;
+                    T v = F::sub((T)0, (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0);
+                    negL[j] = v; mu[j] = v;
                 }
             }
         }
@@ -253,18 +308,18 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
             bool finished_now = false, conv = false;
             if (!(done && n == p.max_iters)) {
                 bool unsat;
-                if (n == p.max_iters) unsat = (h == 0) ? synd_phase<C, T, 0>(lam, i) : synd_phase<C, T, 1>(lam, i);
-                else unsat = (h == 0) ? cn_phase<C, T, 0>(ne, lam, i) : cn_phase<C, T, 1>(ne, lam, i);
+                if (n == p.max_iters) unsat = (h == 0) ? synd_phase<C, T, 0>(mu, i, one) : synd_phase<C, T, 1>(mu, i, one);
+                else unsat = (h == 0) ? cn_phase<C, T, 0>(ne, mu, i, one) : cn_phase<C, T, 1>(ne, mu, i, one);
                 bool any = bar_or(bar, TPF, unsat);
                 if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
             }
             if (finished_now) {
                 // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
                 done = true;
-                const T *src = conv ? lam : L;
+                const T *src = conv ? mu : negL;
                 unsigned int errs = 0;
                 for (int w = wif; w < W; w += WPF) {
-                    unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] > (T)0);
+                    unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] < (T)0);   // lam > 0 <=> -lam < 0
                     if (lane == 0) {
                         if (p.bits) p.bits[(size_t)f * W + w] = word;
                         int lo = 32 * w;
@@ -281,7 +336,7 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
                     c_berr += errs;
                     if (tf == 0) { c_frames++; c_ferr += anyerr; c_iters += n; c_unconv += !conv; }
                 } else if (!p.early_exit) {
-                    bar_sync(bar, TPF);          // snapshot reads of lam before the next stage-0 writes
+                    bar_sync(bar, TPF);          // snapshot reads of mu before the next stage-0 writes
                 }
             }
             if (n == p.max_iters || (done && p.early_exit)) break;
@@ -289,7 +344,7 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
             // ---- variable phase: lam' = L + sum ne', right fold (Orig.hs:95-98) ----
             static_for<C::MAXCD>([&](auto qi) {
                 constexpr int Q = decltype(qi)::value;
-                if (h == 0) vn_stage<C, T, 0, Q>(ne, lam, L, i); else vn_stage<C, T, 1, Q>(ne, lam, L, i);
+                if (h == 0) vn_stage<C, T, 0, Q>(ne, mu, negL, i, one); else vn_stage<C, T, 1, Q>(ne, mu, negL, i, one);
                 bar_sync(bar, TPF);
             });
         }
@@ -411,6 +466,7 @@ int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_f
         return LDPC_B200_EINVAL;
     }
     ResidentParams p = {};
+    p.c_one = 1;
     p.llr = src; p.bits = d_bits_packed; p.iters = d_iters; p.conv = d_conv; p.counters = nullptr;
     p.n_frames = (unsigned int)n_frames; p.max_iters = max_iters; p.early_exit = early_exit;
     p.k_info = 0; p.n_tx = N;
@@ -425,6 +481,7 @@ int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float
     const uint64_t chunk = 1ull << 30;
     for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk) {
         ResidentParams p = {};
+        p.c_one = 1;
         p.llr = nullptr; p.bits = nullptr; p.iters = nullptr; p.conv = nullptr;
         p.counters = (unsigned long long *)d_counters;
         p.n_frames = (unsigned int)std::min<uint64_t>(chunk, n_frames - f0);

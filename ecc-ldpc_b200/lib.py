@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libldpc_b200.so")
+SO_PATH = os.environ.get("LDPC_B200_SO") or os.path.join(_HERE, "libldpc_b200.so")   # env override: kernel-variant experiments
 
 ALGO_SPA, ALGO_MINSUM = 0, 1
 PREC_FP64, PREC_FP32 = 0, 1
