@@ -11,8 +11,8 @@ __global__ void k_generate(T *__restrict__ llr, const uint32_t *__restrict__ cw,
                            uint64_t seed, uint64_t first_frame, float sigma, float scale)
 {
     int groups = (N + 3) / 4;
-    int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = blockIdx.y;
+    int gidx = blockIdx.y * blockDim.x + threadIdx.x;
+    int f = blockIdx.x;
     if (gidx >= groups || f >= F) return;
     float n[4];
     awgn4(seed, first_frame + (uint64_t)f, (uint32_t)gidx, n);
@@ -35,7 +35,7 @@ int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_t
 {
     int N = d->code->N;
     if (n_frames <= 0) return 0;
-    dim3 grid(((N + 3) / 4 + 127) / 128, n_frames);
+    dim3 grid(n_frames, ((N + 3) / 4 + 127) / 128);     // frames on x: y is limited to 65535
     if (d->precision == LDPC_B200_PREC_FP64)
         k_generate<double><<<grid, 128, 0, d->stream>>>((double *)d_llr, d_codewords, N, n_tx, n_frames, seed, first_frame, sigma, llr_scale);
     else

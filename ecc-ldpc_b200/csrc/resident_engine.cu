@@ -3,33 +3,37 @@
 //
 // Why: the reference's state model moves 3E+3N words per frame and iteration; streamed from
 // HBM that caps a B200 at ~1.06 M frames/s for jpl.4096.4.5 at 20 iterations.  Here a frame costs HBM only
-// its LLRs in and its packed decisions out; the binding resources are the ALU pipe and shared memory.
+// its LLRs in and its packed decisions out; the binding resources are instruction issue, the ALU pipe and
+// shared-memory bandwidth.
 //
-// Mapping (SZ = circulant size, one frame = 2*SZ threads):
-//   * thread (h, i): check position i of the block rows of half h (tables in qc_tables.inc; the split gives
-//     both halves 78 of the 156 circulants).  Its check->variable messages ne[] live in REGISTERS for the
+// Mapping (SZ = circulant size, NP = threads per check position, one frame = NP*SZ threads):
+//   * thread (part, i): check position i of the block rows of its part (tables in qc_tables.inc; the split gives
+//     every part the same number of circulants).  Its check->variable messages ne[] live in REGISTERS for the
 //     whole decode (one register per edge, compile-time indexed after full unrolling).
-//   * posteriors lam[N] and channel LLRs L[N] live in SHARED memory.  Circulant (r,k) with shift s connects
+//   * the negated posterior mu = -lam and negL = -L live in SHARED memory.  Circulant (r,k) with shift s connects
 //     check (r,i) to variable (c, (i+s) mod SZ): a warp reads/writes 32 consecutive words -> conflict-free.
-//   * check phase  (Min.hs:75-89 in the two-minimum form of Model.hs:326-343): x = ne - lam gathered from
-//     smem, running min1/min2 and sign parity, syndrome parity of hard(lam) on the fly (Orig.hs:73-78);
-//     then ne' = -3/4 * sign * (|x| == min1 ? min2 : min1) in place.
+//     Every block column is a SZ*sizeof(T)-aligned block, so the rotated address is formed with one add and one
+//     bit-select (LOP3); shifts are compile-time constants and the 67 shift-0 circulants cost nothing.
+//   * check phase (Min.hs:75-89): x = ne + mu gathered from smem; syndrome parity = xor of the sign bits of mu
+//     (Orig.hs:73-78); leave-one-out reduction with the reference's min' operator (one FMNMX.XORSIGN each) in a
+//     binary tree; ne' = -3/4 * (reduction of the others), in place.
 //   * vote: barrier.red.or over the frame's threads = "syndrome all zero?"  (Orig.hs:68-69).
-//   * variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in place
-//     in smem in MAXCD stages: stage q adds, for every block column, the message of its q-th LAST block
-//     row.  Within a stage every address is touched by exactly one thread; a barrier separates stages.
-//     This is exactly the reference's right fold, so the fp64 instance reproduces the reference bit for bit.
+//   * variable phase (Orig.hs:95-98): the right fold ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in place in
+//     smem, one link per stage from the innermost outwards.  Within a stage every address is touched by exactly
+//     one thread; a barrier separates stages; which link of which column runs in which stage is scheduled offline
+//     (tools/gen_qc_tables.py) so that the parts carry equal work in every stage.  Same association as the
+//     reference, so the fp64 instance reproduces the reference bit for bit.
 //   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs).
 //
-// fp32 is the production instance (2 CTAs/SM); fp64 exists to prove the index logic bit-exactly.
+// fp32 is the production instance; fp64 exists to prove the index logic bit-exactly.
 #include "common.cuh"
 #include "philox.cuh"
 #include <utility>
 
-// Tuning switch: RES_ADDR_IMAD 1 = form the rotated word index (i + s) on the FMA pipe (IMAD with an opaque
-// multiplier 1) instead of the ALU pipe, which is the binding unit of this kernel.
-#ifndef RES_ADDR_IMAD
-#define RES_ADDR_IMAD 0
+// RES_PARTS: threads per check position (2 or 4). More parts = fewer message registers per thread = more resident
+// warps to hide shared-memory latency, at the price of more barrier participants.
+#ifndef RES_PARTS
+#define RES_PARTS 2
 #endif
 
 namespace ldpc {
@@ -47,16 +51,13 @@ __device__ __forceinline__ void static_for(F &&f)
     static_for_impl(std::make_integer_sequence<int, N>{}, f);
 }
 
+// Arithmetic with explicit rounding (no FMA contraction), bit access, and shared-memory access by 32-bit shared
+// address + compile-time byte offset (so that the block-column offset rides in the instruction's immediate).
 template <typename T> struct FB;
 template <> struct FB<float> {
     typedef uint32_t B;
     static constexpr B SIGN = 0x80000000u;
     static __device__ __forceinline__ B bits(float x) { return __float_as_uint(x); }
-    static __device__ __forceinline__ float val(B b) { return __uint_as_float(b); }
-    static __device__ __forceinline__ float inf() { return __uint_as_float(0x7f800000u); }
-    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
-    static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
-    static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -67,26 +68,41 @@ template <> struct FB<float> {
         asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
         return r;
     }
+    template <int OFF> static __device__ __forceinline__ float lds(uint32_t addr)
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+        return v;
+    }
+    template <int OFF> static __device__ __forceinline__ void sts(uint32_t addr, float v)
+    {
+        asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v));
+    }
 };
 template <> struct FB<double> {
     typedef unsigned long long B;
     static constexpr B SIGN = 0x8000000000000000ull;
     static __device__ __forceinline__ B bits(double x) { return (B)__double_as_longlong(x); }
-    static __device__ __forceinline__ double val(B b) { return __longlong_as_double((long long)b); }
-    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
-    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
-    static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
-    static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double box(double a, double b)
     {
-        return val(bits(fmin(fabs(a), fabs(b))) | ((bits(a) ^ bits(b)) & SIGN));
+        return __longlong_as_double((long long)(bits(fmin(fabs(a), fabs(b))) | ((bits(a) ^ bits(b)) & SIGN)));
+    }
+    template <int OFF> static __device__ __forceinline__ double lds(uint32_t addr)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+        return v;
+    }
+    template <int OFF> static __device__ __forceinline__ void sts(uint32_t addr, double v)
+    {
+        asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v));
     }
 };
 
-// Compile-time layout of the per-thread message registers: the rows of a half, in order, each with row_deg slots.
+// Compile-time layout of the per-thread message registers: the rows of a part, in order, each with row_deg slots.
 template <class C> struct QcMap {
     static __host__ __device__ constexpr int reg_base(int r)
     {
@@ -98,13 +114,19 @@ template <class C> struct QcMap {
         }
         return -1;
     }
-    static __host__ __device__ constexpr int half_edges(int h)
+    static __host__ __device__ constexpr int part_edges(int h)
     {
         int b = 0;
         for (int q = 0; q < C::HR; q++) b += C::row_deg[C::half_rows[h][q]];
         return b;
     }
-    static constexpr int NEH = half_edges(0) > half_edges(1) ? half_edges(0) : half_edges(1);
+    static __host__ __device__ constexpr int max_part_edges()
+    {
+        int m = 0;
+        for (int h = 0; h < C::NP; h++) m = part_edges(h) > m ? part_edges(h) : m;
+        return m;
+    }
+    static constexpr int NEH = max_part_edges();
     static constexpr int N = C::BC * C::SZ;
 };
 
@@ -120,25 +142,24 @@ __device__ __forceinline__ bool bar_or(int id, int nthreads, bool pred)
     return r != 0;
 }
 
-template <class C>
-__device__ __forceinline__ int var_pos(int i, int s, int one)
+// Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
+// BLK = SZ*sizeof(T) bytes and BLK-aligned, so only the low log2(BLK) bits rotate: one add + one bit-select.
+template <class C, typename T, int S>
+__device__ __forceinline__ uint32_t rot(uint32_t P)
 {
-    if (s == 0) return i;
-#if RES_ADDR_IMAD
-    int t;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(i), "r"(one), "r"(s));
-    return t & (C::SZ - 1);
-#else
-    (void)one;
-    return (i + s) & (C::SZ - 1);
-#endif
+    constexpr uint32_t MASK = C::SZ * sizeof(T) - 1;
+    if constexpr (S == 0) return P;
+    else {
+        uint32_t y = P + S * (uint32_t)sizeof(T), z;
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(z) : "r"(P), "r"(y), "n"(MASK));   // (P & ~MASK) | (y & MASK)
+        return z;
+    }
 }
 
 // Leave-one-out "box" reduction over the D messages of a check row with a binary tree: `build` reduces subtrees
 // bottom-up, `down` hands every leaf the reduction of everything outside it.  The operator is the reference's
 // min' (Min.hs:89: sign product times minimum magnitude), exact in floating point and associative, so the result
-// equals foldr1 min' over the other entries bit for bit.  ~2.7 ops per edge at depth log2(D); the serial
-// min1/min2 recurrence needs a compare+select and two sign operations per edge on top.
+// equals foldr1 min' over the other entries bit for bit.  ~2.6 ops per edge at depth log2(D).
 template <typename T, int LO, int HI> struct BoxTree {
     static constexpr int MID = (LO + HI) / 2;
     BoxTree<T, LO, MID> l;
@@ -172,11 +193,13 @@ template <typename T, int LO> struct BoxTree<T, LO, LO + 1> {
 // -0, and negL = 0 - L is never -0).  Hence hard(lam) = (lam > 0) = sign bit of mu, and the syndrome parity of a
 // check row is the xor of the sign bits of its mu's: half a LOP3 per edge instead of a compare per edge.
 
-// Check-node phase for the rows of half H. Returns true if any of this thread's checks is unsatisfied by hard(lam).
+// Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
+// checks is unsatisfied by hard(lam).
 template <class C, typename T, int H>
-__device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__restrict__ mu, int i, int one)
+__device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], uint32_t P)
 {
     typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
     typename F::B unsat = 0;
     static_for<C::HR>([&](auto qi) {
         constexpr int r = C::half_rows[H][decltype(qi)::value];
@@ -187,7 +210,7 @@ __device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__rest
             constexpr int k = decltype(ki)::value;
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
-            T m = mu[c * C::SZ + var_pos<C>(i, s, one)];
+            T m = F::template lds<c * BLK>(rot<C, T, s>(P));
             par ^= F::bits(m);
             ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
         });
@@ -202,9 +225,10 @@ __device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], const T *__rest
 
 // Syndrome only (used for the test after the last iteration).
 template <class C, typename T, int H>
-__device__ __forceinline__ bool synd_phase(const T *__restrict__ mu, int i, int one)
+__device__ __forceinline__ bool synd_phase(uint32_t P)
 {
     typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
     typename F::B unsat = 0;
     static_for<C::HR>([&](auto qi) {
         constexpr int r = C::half_rows[H][decltype(qi)::value];
@@ -212,32 +236,33 @@ __device__ __forceinline__ bool synd_phase(const T *__restrict__ mu, int i, int 
         typename F::B par = 0;
         static_for<d>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
-            constexpr int c = C::row_col[r][k];
-            constexpr int s = C::row_shift[r][k];
-            par ^= F::bits(mu[c * C::SZ + var_pos<C>(i, s, one)]);
+            par ^= F::bits(F::template lds<C::row_col[r][k] * BLK>(rot<C, T, C::row_shift[r][k]>(P)));
         });
         unsat |= par;
     });
     return (unsat & F::SIGN) != 0;
 }
 
-// Variable-node stage Q for half H: every block column adds the message of its Q-th last block row (in negated
-// form: mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the exact negation of Orig.hs:95-98).
+// Variable-node stage Q for part H.  Column c builds mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the
+// exact negation of Orig.hs:95-98, one link per stage from the innermost (last block row) outwards; col_stage
+// says which link runs in which stage.  negL sits N*sizeof(T) bytes after mu.
 template <class C, typename T, int H, int Q>
-__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], T *__restrict__ mu, const T *__restrict__ negL, int i, int one)
+__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t P)
 {
     typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
+    constexpr int NEGL = QcMap<C>::N * sizeof(T);
     static_for<C::BC>([&](auto ci) {
         constexpr int c = decltype(ci)::value;
-        if constexpr (Q < C::col_deg[c]) {
-            constexpr int r = C::col_row_desc[c][Q];
+        constexpr int step = C::col_stage[c][Q];          // which link of column c's chain runs in this stage
+        if constexpr (step >= 0) {
+            constexpr int r = C::col_row_desc[c][step];
             if constexpr (C::half_of_row[r] == H) {
-                constexpr int k = C::col_k_desc[c][Q];
-                constexpr int s = C::row_shift[r][k];
+                constexpr int k = C::col_k_desc[c][step];
                 constexpr int e = QcMap<C>::reg_base(r) + k;
-                int idx = c * C::SZ + var_pos<C>(i, s, one);
-                T acc = (Q == 0) ? negL[idx] : mu[idx];
-                mu[idx] = F::sub(acc, ne[e]);
+                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
+                T acc = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * BLK>(a);
+                F::template sts<c * BLK>(a, F::sub(acc, ne[e]));
             }
         }
     });
@@ -256,33 +281,92 @@ struct ResidentParams {
     float sigma, scale;
     int n_tx, k_info;
     unsigned long long seed, first_frame;
-    int c_one;                     // = 1: opaque multiplier for RES_ADDR_IMAD
 };
 
+struct FrameCounters {
+    unsigned long long frames = 0, ferr = 0, berr = 0, iters = 0, unconv = 0;
+};
+
+// Decode of one frame by the threads of part H (the iteration loop is instantiated per part so that no dispatch
+// happens inside it; all parts execute the same sequence of named barriers).
+template <class C, typename T, int H>
+__device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned int f, const T *mu, const T *negL, uint32_t P,
+                                             int bar, int tf, int lane, FrameCounters &cnt)
+{
+    typedef QcMap<C> Mp;
+    constexpr int N = Mp::N, TPF = C::NP * C::SZ, WPF = TPF / 32, W = N / 32;
+    const int wif = tf >> 5;
+    T ne[Mp::NEH];
+#pragma unroll
+    for (int e = 0; e < Mp::NEH; e++) ne[e] = (T)0;               // orig_ne = 0 (Orig.hs:64-65)
+
+    bool done = false;
+    for (int n = 0;; n++) {
+        bool finished_now = false, conv = false;
+        if (!(done && n == p.max_iters)) {
+            bool unsat = (n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H>(ne, P);
+            bool any = bar_or(bar, TPF, unsat);
+            if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
+        }
+        if (finished_now) {
+            // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
+            done = true;
+            const T *src = conv ? mu : negL;
+            unsigned int errs = 0;
+            for (int w = wif; w < W; w += WPF) {
+                unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] < (T)0);   // lam > 0 <=> -lam < 0
+                if (lane == 0) {
+                    if (p.bits) p.bits[(size_t)f * W + w] = word;
+                    int lo = 32 * w;
+                    if (lo + 32 <= p.k_info) errs += __popc(word);
+                    else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
+                }
+            }
+            if (tf == 0) {
+                if (p.iters) p.iters[f] = n;
+                if (p.conv) p.conv[f] = conv ? 1 : 0;
+            }
+            if (p.counters) {
+                bool anyerr = bar_or(bar, TPF, errs != 0);
+                cnt.berr += errs;
+                if (tf == 0) { cnt.frames++; cnt.ferr += anyerr; cnt.iters += n; cnt.unconv += !conv; }
+            } else if (!p.early_exit) {
+                bar_sync(bar, TPF);          // snapshot reads of mu before the next stage-0 writes
+            }
+        }
+        if (n == p.max_iters || (done && p.early_exit)) break;
+
+        // ---- variable phase ----
+        static_for<C::MAXCD>([&](auto qi) {
+            vn_stage<C, T, H, decltype(qi)::value>(ne, P);
+            bar_sync(bar, TPF);
+        });
+    }
+}
+
 template <class C, typename T, int FPC>
-__global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_resident(ResidentParams p)
+__global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k_resident(ResidentParams p)
 {
     typedef QcMap<C> Mp;
     typedef FB<T> F;
-    constexpr int N = Mp::N, SZ = C::SZ, TPF = 2 * SZ, WPF = TPF / 32, W = N / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = Mp::N, SZ = C::SZ, TPF = C::NP * SZ;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF;
-    const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31, wif = tf >> 5;
+    const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31;
     const int bar = slot + 1;
     T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;      // negated posterior, see above
     T *negL = mu + N;                                                    // negated channel LLRs
-    const int one = p.c_one;
     unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N);
+    const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
 
-    unsigned long long c_frames = 0, c_ferr = 0, c_berr = 0, c_iters = 0, c_unconv = 0;
-
+    FrameCounters cnt;
     for (;;) {
         if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
         bar_sync(bar, TPF);
         const unsigned int f = s_next[slot];
         if (f >= p.n_frames) break;
 
-        // ---- frame in: channel LLRs -> L, lam ; messages = 0 (Orig.hs:64-65) ----
+        // ---- frame in: negL = 0 - L, mu = negL ----
         if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
             for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
@@ -298,64 +382,25 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
                 }
             }
         }
-        T ne[Mp::NEH];
-#pragma unroll
-        for (int e = 0; e < Mp::NEH; e++) ne[e] = (T)0;
         bar_sync(bar, TPF);
 
-        bool done = false;
-        for (int n = 0;; n++) {
-            bool finished_now = false, conv = false;
-            if (!(done && n == p.max_iters)) {
-                bool unsat;
-                if (n == p.max_iters) unsat = (h == 0) ? synd_phase<C, T, 0>(mu, i, one) : synd_phase<C, T, 1>(mu, i, one);
-                else unsat = (h == 0) ? cn_phase<C, T, 0>(ne, mu, i, one) : cn_phase<C, T, 1>(ne, mu, i, one);
-                bool any = bar_or(bar, TPF, unsat);
-                if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
-            }
-            if (finished_now) {
-                // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
-                done = true;
-                const T *src = conv ? mu : negL;
-                unsigned int errs = 0;
-                for (int w = wif; w < W; w += WPF) {
-                    unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] < (T)0);   // lam > 0 <=> -lam < 0
-                    if (lane == 0) {
-                        if (p.bits) p.bits[(size_t)f * W + w] = word;
-                        int lo = 32 * w;
-                        if (lo + 32 <= p.k_info) errs += __popc(word);
-                        else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
-                    }
-                }
-                if (tf == 0) {
-                    if (p.iters) p.iters[f] = n;
-                    if (p.conv) p.conv[f] = conv ? 1 : 0;
-                }
-                if (p.counters) {
-                    bool anyerr = bar_or(bar, TPF, errs != 0);
-                    c_berr += errs;
-                    if (tf == 0) { c_frames++; c_ferr += anyerr; c_iters += n; c_unconv += !conv; }
-                } else if (!p.early_exit) {
-                    bar_sync(bar, TPF);          // snapshot reads of mu before the next stage-0 writes
-                }
-            }
-            if (n == p.max_iters || (done && p.early_exit)) break;
-
-            // ---- variable phase: lam' = L + sum ne', right fold (Orig.hs:95-98) ----
-            static_for<C::MAXCD>([&](auto qi) {
-                constexpr int Q = decltype(qi)::value;
-                if (h == 0) vn_stage<C, T, 0, Q>(ne, mu, negL, i, one); else vn_stage<C, T, 1, Q>(ne, mu, negL, i, one);
-                bar_sync(bar, TPF);
-            });
+        if constexpr (C::NP == 2) {
+            if (h == 0) decode_frame<C, T, 0>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 1>(p, f, mu, negL, P, bar, tf, lane, cnt);
+        } else {
+            if (h == 0) decode_frame<C, T, 0>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 1) decode_frame<C, T, 1>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 2) decode_frame<C, T, 2>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 3>(p, f, mu, negL, P, bar, tf, lane, cnt);
         }
         // all smem reads of this frame are done before the next frame's loads: the bar_sync after s_next does it
     }
 
     if (p.counters) {
-        if (lane == 0 && c_berr) atomicAdd(&p.counters[2], c_berr);
-        if (tf == 0 && c_frames) {
-            atomicAdd(&p.counters[0], c_frames); atomicAdd(&p.counters[1], c_ferr);
-            atomicAdd(&p.counters[3], c_iters); atomicAdd(&p.counters[4], c_unconv);
+        if (lane == 0 && cnt.berr) atomicAdd(&p.counters[2], cnt.berr);
+        if (tf == 0 && cnt.frames) {
+            atomicAdd(&p.counters[0], cnt.frames); atomicAdd(&p.counters[1], cnt.ferr);
+            atomicAdd(&p.counters[3], cnt.iters); atomicAdd(&p.counters[4], cnt.unconv);
         }
     }
 }
@@ -363,6 +408,14 @@ __global__ void __launch_bounds__(FPC * 2 * C::SZ, sizeof(T) == 4 ? 2 : 1) k_res
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+
+#if RES_PARTS == 2
+typedef QcJpl1024P2 QcJpl1024;
+typedef QcJpl4096P2 QcJpl4096;
+#else
+typedef QcJpl1024P4 QcJpl1024;
+typedef QcJpl4096P4 QcJpl4096;
+#endif
 
 template <class C>
 static bool matches(const ldpc_b200_code *c)
@@ -407,12 +460,13 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
     typedef QcMap<C> Mp;
     auto kern = k_resident<C, T, FPC>;
     size_t smem = (size_t)FPC * 2 * Mp::N * sizeof(T) + FPC * sizeof(unsigned int);
+    static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
     static thread_local int blocks_per_sm = 0;
     static thread_local int n_sm = 0;
     if (!blocks_per_sm) {
         LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FPC * 2 * C::SZ, smem));
+        LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FPC * C::NP * C::SZ, smem));
         LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->code->device));
         if (blocks_per_sm < 1) { set_error("RESIDENT kernel does not fit on this device"); blocks_per_sm = 0; return LDPC_B200_EUNSUPPORTED; }
     }
@@ -422,7 +476,7 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
     unsigned int groups = (p.n_frames + FPC - 1) / FPC;
     unsigned int grid = std::min<unsigned int>(groups, (unsigned int)(blocks_per_sm * n_sm));
     if (grid == 0) return 0;
-    kern<<<grid, FPC * 2 * C::SZ, smem, d->stream>>>(p);
+    kern<<<grid, FPC * C::NP * C::SZ, smem, d->stream>>>(p);
     d->launches++;
     LDPC_CUDA(cudaGetLastError());
     return 0;
@@ -466,7 +520,7 @@ int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_f
         return LDPC_B200_EINVAL;
     }
     ResidentParams p = {};
-    p.c_one = 1;
+    
     p.llr = src; p.bits = d_bits_packed; p.iters = d_iters; p.conv = d_conv; p.counters = nullptr;
     p.n_frames = (unsigned int)n_frames; p.max_iters = max_iters; p.early_exit = early_exit;
     p.k_info = 0; p.n_tx = N;
@@ -481,7 +535,7 @@ int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float
     const uint64_t chunk = 1ull << 30;
     for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk) {
         ResidentParams p = {};
-        p.c_one = 1;
+        
         p.llr = nullptr; p.bits = nullptr; p.iters = nullptr; p.conv = nullptr;
         p.counters = (unsigned long long *)d_counters;
         p.n_frames = (unsigned int)std::min<uint64_t>(chunk, n_frames - f0);
