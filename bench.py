@@ -270,6 +270,22 @@ def main():
     # ---------------- extra operating points with early exit (reference semantics) ----------------
     extra = {}
     if not args.no_extra:
+        # float32 LLRs in / packed decisions out: half the PCIe bytes of the reference-typed call
+        h32 = torch.empty((Be, code.N), dtype=torch.float32).pin_memory()
+        h32.copy_(d_llr[:Be].cpu())
+        hpk = torch.empty((Be, W), dtype=torch.int32).pin_memory()
+
+        def step_e2e32():
+            lib.check(L.ldpc_b200_decode_f32(dec.h, MAX_ITERS, Be, h32.data_ptr(), hpk.data_ptr(), h_iters.data_ptr(), h_conv.data_ptr()))
+        step_e2e32()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e32()
+        torch.cuda.synchronize()
+        dt32 = time.perf_counter() - t0
+        extra["e2e_f32_packed"] = {"info_gbit_per_s": Be * e2e_steps / dt32 * code.K / 1e9, "h2d_bytes_per_step": Be * code.N * 4,
+                                   "d2h_bytes_per_step": Be * (W * 4 + 5), "api": "ldpc_b200_decode_f32", "ranks_timed": 1}
         for ebn0 in (3.5, 4.0, 4.5):
             gen(ebn0, rank * B)
             d_cnt.zero_()

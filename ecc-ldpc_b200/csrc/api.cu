@@ -296,6 +296,13 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
     stream_free(d);
     cudaFree(d->d_in); cudaFree(d->d_bits); cudaFree(d->d_iters); cudaFree(d->d_conv); cudaFree(d->d_counters);
     cudaFree(d->res_work); cudaFree(d->res_conv_buf);
+    for (int k = 0; k < 2; k++) {
+        ldpc_b200_decoder::PipeSet &s = d->pipe[k];
+        if (k == 1) { cudaFree(s.d_in); cudaFree(s.d_bits); cudaFree(s.d_iters); cudaFree(s.d_conv); }
+        cudaFree(s.d_bytes);
+        if (s.h2d_done) { cudaEventDestroy(s.h2d_done); cudaEventDestroy(s.d2h_done); cudaEventDestroy(s.t0); cudaEventDestroy(s.t1); }
+    }
+    if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
     if (d->h_pinned) cudaFreeHost(d->h_pinned);
     cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
     cudaStreamDestroy(d->stream); cudaStreamDestroy(d->copy_stream);
@@ -337,44 +344,95 @@ int ldpc_b200_decode_device(ldpc_b200_decoder_t *d, int max_iters, int early_exi
     return rc;
 }
 
-// Shared body of the two host-buffer entry points.
+static const int PIPE_CHUNK_MAX = 4096;
+
+static int ensure_pipe(ldpc_b200_decoder *d, bool want_bytes)
+{
+    int rc = ensure_staging(d);
+    if (rc) return rc;
+    int N = d->code->N;
+    if (!d->d2h_stream) LDPC_CUDA(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        ldpc_b200_decoder::PipeSet &s = d->pipe[k];
+        if (!s.h2d_done) {
+            LDPC_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+            LDPC_CUDA(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+            LDPC_CUDA(cudaEventCreate(&s.t0));
+            LDPC_CUDA(cudaEventCreate(&s.t1));
+            s.frames = std::min(d->max_batch, PIPE_CHUNK_MAX);
+            if (k == 0) {              // set 0 aliases the decoder's own staging (sized for max_batch)
+                s.d_in = d->d_in; s.d_bits = d->d_bits; s.d_iters = d->d_iters; s.d_conv = d->d_conv;
+            } else {
+                LDPC_CUDA(cudaMalloc(&s.d_in, (size_t)s.frames * N * sizeof(double)));
+                LDPC_CUDA(cudaMalloc(&s.d_bits, (size_t)s.frames * words_per_frame(N) * sizeof(uint32_t)));
+                LDPC_CUDA(cudaMalloc(&s.d_iters, (size_t)s.frames * sizeof(int32_t)));
+                LDPC_CUDA(cudaMalloc(&s.d_conv, (size_t)s.frames));
+            }
+        }
+        if (want_bytes && !s.d_bytes) LDPC_CUDA(cudaMalloc(&s.d_bytes, (size_t)s.frames * N));
+    }
+    return 0;
+}
+
+// Shared body of the two host-buffer entry points: frames go through in chunks on three streams so that the
+// H2D copy of chunk k+1, the decode of chunk k and the D2H copy of chunk k-1 overlap (pinned host buffers make
+// the copies truly asynchronous; pageable ones still work).
 static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const void *llr, bool is_double,
                        uint8_t *bits_bytes, uint32_t *bits_packed, int32_t *iters, uint8_t *converged)
 {
     if (!d || max_iters < 0 || n_frames < 0 || (n_frames && (!llr || (!bits_bytes && !bits_packed)))) { set_error("decode: bad arguments"); return LDPC_B200_EINVAL; }
     if (n_frames == 0) return 0;
     LDPC_CUDA(cudaSetDevice(d->code->device));
-    int rc = ensure_staging(d);
+    int rc = ensure_pipe(d, bits_bytes != nullptr);
     if (rc) return rc;
     int N = d->code->N, W = words_per_frame(N);
     size_t in_es = is_double ? sizeof(double) : sizeof(float);
-    uint8_t *d_bytes = nullptr;
-    if (bits_bytes) LDPC_CUDA(cudaMalloc(&d_bytes, (size_t)std::min(n_frames, d->max_batch) * N));
+    int cap = d->pipe[0].frames;
+    int chunk = std::max(256, (n_frames + 3) / 4);
+    chunk = std::min(chunk, cap);
     double total_ms = 0.0;
     int64_t total_launches = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += d->max_batch) {
-        int F = std::min(d->max_batch, n_frames - f0);
-        LDPC_CUDA(cudaMemcpyAsync(d->d_in, (const char *)llr + (size_t)f0 * N * in_es, (size_t)F * N * in_es, cudaMemcpyHostToDevice, d->stream));
-        begin_timing(d);
-        rc = decode_dispatch(d, max_iters, 1, F, d->d_in, is_double, d->d_bits, d->d_iters, d->d_conv);
+    auto harvest = [&](ldpc_b200_decoder::PipeSet &s) -> int {
+        if (!s.timing_pending) return 0;
+        LDPC_CUDA(cudaEventSynchronize(s.d2h_done));
+        float ms = 0.f;
+        LDPC_CUDA(cudaEventElapsedTime(&ms, s.t0, s.t1));
+        total_ms += ms;
+        s.timing_pending = false;
+        return 0;
+    };
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames && !rc; f0 += chunk, k++) {
+        int F = std::min(chunk, n_frames - f0);
+        ldpc_b200_decoder::PipeSet &s = d->pipe[k & 1];
+        rc = harvest(s);                         // also guarantees the set's buffers are free again
         if (rc) break;
-        if (bits_bytes) {
-            rc = unpack_bits(d, F, d->d_bits, d_bytes);
-            if (rc) break;
-        }
-        end_timing(d);
-        if (bits_bytes) LDPC_CUDA(cudaMemcpyAsync(bits_bytes + (size_t)f0 * N, d_bytes, (size_t)F * N, cudaMemcpyDeviceToHost, d->stream));
-        if (bits_packed) LDPC_CUDA(cudaMemcpyAsync(bits_packed + (size_t)f0 * W, d->d_bits, (size_t)F * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
-        if (iters) LDPC_CUDA(cudaMemcpyAsync(iters + f0, d->d_iters, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
-        if (converged) LDPC_CUDA(cudaMemcpyAsync(converged + f0, d->d_conv, (size_t)F, cudaMemcpyDeviceToHost, d->stream));
-        LDPC_CUDA(cudaStreamSynchronize(d->stream));
-        finish_timing(d);
-        total_ms += d->last_ms;
-        total_launches += d->last_launches;
+        LDPC_CUDA(cudaMemcpyAsync(s.d_in, (const char *)llr + (size_t)f0 * N * in_es, (size_t)F * N * in_es, cudaMemcpyHostToDevice, d->copy_stream));
+        LDPC_CUDA(cudaEventRecord(s.h2d_done, d->copy_stream));
+        LDPC_CUDA(cudaStreamWaitEvent(d->stream, s.h2d_done, 0));
+        d->launches = 0;
+        LDPC_CUDA(cudaEventRecord(s.t0, d->stream));
+        rc = decode_dispatch(d, max_iters, 1, F, s.d_in, is_double, s.d_bits, s.d_iters, s.d_conv);
+        if (!rc && bits_bytes) rc = unpack_bits(d, F, s.d_bits, s.d_bytes);
+        if (rc) break;
+        LDPC_CUDA(cudaEventRecord(s.t1, d->stream));
+        total_launches += d->launches;
+        LDPC_CUDA(cudaStreamWaitEvent(d->d2h_stream, s.t1, 0));
+        if (bits_bytes) LDPC_CUDA(cudaMemcpyAsync(bits_bytes + (size_t)f0 * N, s.d_bytes, (size_t)F * N, cudaMemcpyDeviceToHost, d->d2h_stream));
+        if (bits_packed) LDPC_CUDA(cudaMemcpyAsync(bits_packed + (size_t)f0 * W, s.d_bits, (size_t)F * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->d2h_stream));
+        if (iters) LDPC_CUDA(cudaMemcpyAsync(iters + f0, s.d_iters, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, d->d2h_stream));
+        if (converged) LDPC_CUDA(cudaMemcpyAsync(converged + f0, s.d_conv, (size_t)F, cudaMemcpyDeviceToHost, d->d2h_stream));
+        LDPC_CUDA(cudaEventRecord(s.d2h_done, d->d2h_stream));
+        s.timing_pending = true;
     }
-    if (d_bytes) cudaFree(d_bytes);
+    for (int q = 0; q < 2; q++) {
+        int r2 = harvest(d->pipe[q]);
+        if (!rc) rc = r2;
+    }
+    if (rc) { cudaStreamSynchronize(d->copy_stream); cudaStreamSynchronize(d->stream); cudaStreamSynchronize(d->d2h_stream); }
     d->last_ms = total_ms;
     d->last_launches = total_launches;
+    d->timing_pending = false;
     return rc;
 }
 

@@ -72,6 +72,15 @@ struct ldpc_b200_decoder {
     int64_t last_launches = 0;
     int64_t launches = 0;        // running count within a call
     bool timing_pending = false;
+    // second staging set + stream/events for the pipelined host-buffer decode (H2D | decode | D2H overlap)
+    struct PipeSet {
+        void *d_in = nullptr; uint32_t *d_bits = nullptr; uint8_t *d_bytes = nullptr;
+        int32_t *d_iters = nullptr; uint8_t *d_conv = nullptr;
+        cudaEvent_t h2d_done = nullptr, t0 = nullptr, t1 = nullptr, d2h_done = nullptr;
+        int frames = 0;              // capacity in frames
+        bool timing_pending = false;
+    } pipe[2];
+    cudaStream_t d2h_stream = nullptr;
     // RESIDENT engine scratch
     unsigned int *res_work = nullptr;   // persistent-CTA work counter
     void *res_conv_buf = nullptr;       // max_batch x N float, when float64 LLRs feed the fp32 kernel

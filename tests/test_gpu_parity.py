@@ -346,3 +346,15 @@ def test_ecc_record_mirror(gpu_lib, builtin_codes, oracles):
     out, flag = e2.decode(5.0 * (2.0 * e2.encode(m) - 1.0))
     assert flag and np.array_equal(out, m)
     e2.close()
+
+
+def test_simulate_sharded_single_rank(gpu_lib, dcodes, builtin_codes):
+    """shard.simulate_sharded without a process group = plain simulate (the 2-rank case is tests/test_shard_cpu.py + bench --gpus 2)."""
+    from ecc_ldpc_b200 import shard
+    code = builtin_codes["jpl.1024.4.5"]
+    dec = gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp32", max_batch=256)
+    a = shard.simulate_sharded(dec, 20, 3.6, code.K, 1280, 5, 0, 700)
+    b = dec.simulate(20, 3.6, code.K, 1280, 5, 0, 700)
+    for k in shard.COUNTER_NAMES:
+        assert a[k] == b[k]
+    dec.close()
