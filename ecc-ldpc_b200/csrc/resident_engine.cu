@@ -160,20 +160,23 @@ __device__ __forceinline__ uint32_t rot(uint32_t P)
 // bottom-up, `down` hands every leaf the reduction of everything outside it.  The operator is the reference's
 // min' (Min.hs:89: sign product times minimum magnitude), exact in floating point and associative, so the result
 // equals foldr1 min' over the other entries bit for bit.  ~2.6 ops per edge at depth log2(D).
-template <typename T, int LO, int HI> struct BoxTree {
+template <typename T> struct OpBox { static __device__ __forceinline__ T f(T a, T b) { return FB<T>::box(a, b); } };
+template <typename T> struct OpAdd { static __device__ __forceinline__ T f(T a, T b) { return FB<T>::add(a, b); } };
+
+template <typename T, int LO, int HI, class Op = OpBox<T>> struct BoxTree {
     static constexpr int MID = (LO + HI) / 2;
-    BoxTree<T, LO, MID> l;
-    BoxTree<T, MID, HI> r;
+    BoxTree<T, LO, MID, Op> l;
+    BoxTree<T, MID, HI, Op> r;
     T m;
     template <class A> __device__ __forceinline__ void build(const A &a)
     {
         l.build(a); r.build(a);
-        m = FB<T>::box(l.m, r.m);
+        m = Op::f(l.m, r.m);
     }
     template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const
     {
-        l.down(FB<T>::box(o, r.m), emit);
-        r.down(FB<T>::box(o, l.m), emit);
+        l.down(Op::f(o, r.m), emit);
+        r.down(Op::f(o, l.m), emit);
     }
     template <class Fn> __device__ __forceinline__ void down_root(Fn &&emit) const
     {
@@ -181,7 +184,7 @@ template <typename T, int LO, int HI> struct BoxTree {
         r.down(l.m, emit);
     }
 };
-template <typename T, int LO> struct BoxTree<T, LO, LO + 1> {
+template <typename T, int LO, class Op> struct BoxTree<T, LO, LO + 1, Op> {
     T m;
     template <class A> __device__ __forceinline__ void build(const A &a) { m = a(std::integral_constant<int, LO>{}); }
     template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const { emit(std::integral_constant<int, LO>{}, o); }
@@ -193,9 +196,22 @@ template <typename T, int LO> struct BoxTree<T, LO, LO + 1> {
 // -0, and negL = 0 - L is never -0).  Hence hard(lam) = (lam > 0) = sign bit of mu, and the syndrome parity of a
 // check row is the xor of the sign bits of its mu's: half a LOP3 per edge instead of a compare per edge.
 
+// Sum-product in the log domain (fp32 production form of Orig.hs:81-92).  With phi(x) = -ln tanh(x/2) = 2 atanh(e^-x):
+//   -2 atanh'( prod_{j/=n} tanh(x_j/2) )  =  -(prod sign x_j) * phi( sum_{j/=n} phi(|x_j|) ),
+// phi is its own inverse.  The tanh-product form saturates in fp32 (tanhf = 1 beyond |x| ~ 18, then the atanh' clamp
+// jumps to 37.43); the log-domain form stays smooth up to the reference's own ceiling 2 * 18.714973875118524, which
+// is applied as a cap (Utils.hs:113-117).  An exact-zero input gives phi = +inf, hence 0 for all other edges, as
+// the product does.
+__device__ __forceinline__ float spa_phi(float x)
+{
+    float e = __expf(-x);                             // x >= 0
+    return __logf(__fdividef(1.0f + e, 1.0f - e));    // x = 0 -> +inf ; x = +inf -> 0
+}
+static constexpr float SPA_CAP = 37.429947750237048f;
+
 // Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
 // checks is unsatisfied by hard(lam).
-template <class C, typename T, int H>
+template <class C, typename T, int H, int ALGO>
 __device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], uint32_t P)
 {
     typedef FB<T> F;
@@ -215,10 +231,25 @@ __device__ __forceinline__ bool cn_phase(T (&ne)[QcMap<C>::NEH], uint32_t P)
             ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
         });
         unsat |= par;
-        // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
-        BoxTree<T, 0, d> tree;
-        tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
-        tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = F::mul((T)-0.75, others); });
+        if constexpr (ALGO == LDPC_B200_ALGO_MINSUM) {
+            // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
+            BoxTree<T, 0, d> tree;
+            tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
+            tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = F::mul((T)-0.75, others); });
+        } else if constexpr (sizeof(T) == 4) {
+            // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), log-domain form
+            uint32_t sgn = 0;
+            static_for<d>([&](auto ki) { sgn ^= __float_as_uint(ne[base + decltype(ki)::value]); });
+            sgn = ~sgn & 0x80000000u;                                  // leading minus times the product of ALL signs
+            BoxTree<float, 0, d, OpAdd<float>> tree;
+            tree.build([&](auto ki) { return spa_phi(fabsf(ne[base + decltype(ki)::value])); });
+            tree.down_root([&](auto ki, float others) {
+                constexpr int k = decltype(ki)::value;
+                float mag = fminf(spa_phi(others), SPA_CAP);
+                // own sign removed from the product: sgn ^ sign(x_k)
+                ne[base + k] = __uint_as_float(__float_as_uint(mag) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+            });
+        }
     });
     return (unsat & F::SIGN) != 0;
 }
@@ -289,7 +320,7 @@ struct FrameCounters {
 
 // Decode of one frame by the threads of part H (the iteration loop is instantiated per part so that no dispatch
 // happens inside it; all parts execute the same sequence of named barriers).
-template <class C, typename T, int H>
+template <class C, typename T, int H, int ALGO>
 __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned int f, const T *mu, const T *negL, uint32_t P,
                                              int bar, int tf, int lane, FrameCounters &cnt)
 {
@@ -304,7 +335,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
     for (int n = 0;; n++) {
         bool finished_now = false, conv = false;
         if (!(done && n == p.max_iters)) {
-            bool unsat = (n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H>(ne, P);
+            bool unsat = (n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO>(ne, P);
             bool any = bar_or(bar, TPF, unsat);
             if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
         }
@@ -344,7 +375,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
     }
 }
 
-template <class C, typename T, int FPC>
+template <class C, typename T, int FPC, int ALGO>
 __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k_resident(ResidentParams p)
 {
     typedef QcMap<C> Mp;
@@ -385,13 +416,13 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
         bar_sync(bar, TPF);
 
         if constexpr (C::NP == 2) {
-            if (h == 0) decode_frame<C, T, 0>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else decode_frame<C, T, 1>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            if (h == 0) decode_frame<C, T, 0, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 1, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
         } else {
-            if (h == 0) decode_frame<C, T, 0>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else if (h == 1) decode_frame<C, T, 1>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else if (h == 2) decode_frame<C, T, 2>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else decode_frame<C, T, 3>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            if (h == 0) decode_frame<C, T, 0, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 1) decode_frame<C, T, 1, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 2) decode_frame<C, T, 2, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 3, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
         }
         // all smem reads of this frame are done before the next frame's loads: the bar_sync after s_next does it
     }
@@ -444,7 +475,9 @@ int resident_kind_for(const ldpc_b200_code *c)
 
 bool resident_supports(const ldpc_b200_decoder *d)
 {
-    return d->code->resident_kind != 0 && d->algo == LDPC_B200_ALGO_MINSUM;
+    // min-sum: fp32 and fp64; sum-product: fp32 only (fp64 sum-product is the STREAM engine's literal form)
+    return d->code->resident_kind != 0 &&
+           (d->algo == LDPC_B200_ALGO_MINSUM || d->precision == LDPC_B200_PREC_FP32);
 }
 
 template <typename T>
@@ -454,11 +487,11 @@ __global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out
     if (idx < n) out[idx] = (T)in[idx];
 }
 
-template <class C, typename T, int FPC>
+template <class C, typename T, int FPC, int ALGO>
 static int launch(ldpc_b200_decoder *d, ResidentParams &p)
 {
     typedef QcMap<C> Mp;
-    auto kern = k_resident<C, T, FPC>;
+    auto kern = k_resident<C, T, FPC, ALGO>;
     size_t smem = (size_t)FPC * 2 * Mp::N * sizeof(T) + FPC * sizeof(unsigned int);
     static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
     static thread_local int blocks_per_sm = 0;
@@ -482,19 +515,21 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
     return 0;
 }
 
-template <typename T>
+template <typename T, int ALGO>
 static int launch_kind(ldpc_b200_decoder *d, ResidentParams &p)
 {
     switch (d->code->resident_kind) {
-    case 1: return launch<QcJpl1024, T, 4>(d, p);
-    case 2: return launch<QcJpl4096, T, 1>(d, p);
+    case 1: return launch<QcJpl1024, T, 4, ALGO>(d, p);
+    case 2: return launch<QcJpl4096, T, 1, ALGO>(d, p);
     default: set_error("no RESIDENT specialisation for this code"); return LDPC_B200_EUNSUPPORTED;
     }
 }
 
 static int launch_prec(ldpc_b200_decoder *d, ResidentParams &p)
 {
-    return d->precision == LDPC_B200_PREC_FP64 ? launch_kind<double>(d, p) : launch_kind<float>(d, p);
+    if (d->algo == LDPC_B200_ALGO_SPA) return launch_kind<float, LDPC_B200_ALGO_SPA>(d, p);
+    return d->precision == LDPC_B200_PREC_FP64 ? launch_kind<double, LDPC_B200_ALGO_MINSUM>(d, p)
+                                               : launch_kind<float, LDPC_B200_ALGO_MINSUM>(d, p);
 }
 
 int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,

@@ -8,11 +8,12 @@ from ecc_ldpc_b200 import codes, lib
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 name = sys.argv[2] if len(sys.argv) > 2 else "jpl.4096.4.5"
+algo = sys.argv[3] if len(sys.argv) > 3 else "min"
 code = codes.load_builtin(name)
 n_tx = {"jpl.4096.4.5": 5120, "jpl.1024.4.5": 1280}[name]
 lib.init(0)
 dc = lib.DeviceCode(code)
-dec = lib.Decoder(dc, "min", "fp32", max_batch=F)
+dec = lib.Decoder(dc, algo, "fp32", max_batch=F)
 llr = lib.DeviceBuffer(F * code.N * 4)
 bits = lib.DeviceBuffer(F * (code.N // 32) * 4)
 it = lib.DeviceBuffer(F * 4)
@@ -29,4 +30,4 @@ for ebn0, ee in ((2.0, True), (4.0, True)):
     m = float(np.median(ms[3:]))
     avg_it = it.download(np.int32, (F,)).mean()
     out.append("ebn0 %.1f: %.3f ms  %.3f Mframes/s  %.2f Gbit/s  avg_it %.2f" % (ebn0, m, F / m / 1e3, F / m / 1e3 * code.K / 1e3, avg_it))
-print(os.environ.get("LDPC_B200_SO", "default"), "|", " | ".join(out))
+print(os.environ.get("LDPC_B200_SO", "default"), name, algo, "engine", dec.engine(), "|", " | ".join(out))
