@@ -235,3 +235,53 @@ def load_dir(name: str, codes_root: str) -> Code:
     if gcols > p:
         raise ValueError("bad code size match %r" % ((code.K + gcols, code.N),))   # Utils.hs:43-44
     return code
+
+
+# ---------------------------------------------------------------------------------------------
+# Writers: the builtin fixtures back into the reference's file formats (what `codes/` looks like to the C++ loader)
+# ---------------------------------------------------------------------------------------------
+
+def _alist_text(nrows, ncols, rows):
+    """Reference orientation (Alist.hs:12-24 `show`): 'nrows ncols', max weights, row weights, column weights,
+    row lists, column lists (1-based)."""
+    cols = [[] for _ in range(ncols)]
+    for r, cs in enumerate(rows):
+        for c in cs:
+            cols[c].append(r)
+    out = ["%d %d" % (nrows, ncols), "%d %d" % (max(len(r) for r in rows), max(len(c) for c in cols)),
+           " ".join(str(len(r)) for r in rows), " ".join(str(len(c)) for c in cols)]
+    out += [" ".join(str(c + 1) for c in r) for r in rows]
+    out += [" ".join(str(r + 1) for r in c) for c in cols]
+    return "\n".join(out) + "\n"
+
+
+def _q_text(sz, words):
+    return "%d\n" % sz + "".join(" ".join(str(w) for w in row) + " \n" for row in words)
+
+
+def _rows_of(row_ptr, col_idx):
+    return [list(map(int, col_idx[row_ptr[i]:row_ptr[i + 1]])) for i in range(len(row_ptr) - 1)]
+
+
+def write_reference_dir(root, names=("moon.7.13", "jpl.1024.4.5", "jpl.4096.4.5")):
+    """Writes <root>/<name>/{H,G}.{q|alist} for the builtin codes that have a generator. Returns root."""
+    for name in names:
+        code = load_builtin(name)
+        d = os.path.join(root, name)
+        os.makedirs(d, exist_ok=True)
+        if code.is_qc:
+            hw = [[(1 << int(s)) if s >= 0 else 0 for s in row] for row in code.shifts]
+            open(os.path.join(d, "H.q"), "w").write(_q_text(code.sz, hw))
+            open(os.path.join(d, "G.q"), "w").write(_q_text(code.sz, code.g_words))
+        else:
+            open(os.path.join(d, "H.alist"), "w").write(_alist_text(code.M, code.N, _rows_of(code.row_ptr, code.col_idx)))
+            open(os.path.join(d, "G.alist"), "w").write(_alist_text(code.K, code.N - code.K, _rows_of(code.g_row_ptr, code.g_col_idx)))
+    return root
+
+
+def builtin_codes_dir():
+    """A `codes/` directory in the reference's formats, generated once from the JSON fixtures."""
+    root = os.path.join(_CODES_DIR, "_ref_format")
+    if not os.path.isfile(os.path.join(root, "jpl.4096.4.5", "G.q")):
+        write_reference_dir(root)
+    return root

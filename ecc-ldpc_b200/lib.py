@@ -32,6 +32,16 @@ EXPORTS = [
 ]
 
 
+ECC_EXPORTS = [
+    "ldpc_b200_matrix_load", "ldpc_b200_matrix_parse", "ldpc_b200_matrix_destroy", "ldpc_b200_matrix_info",
+    "ldpc_b200_matrix_csr", "ldpc_b200_matrix_qc_shifts", "ldpc_b200_ecc_open", "ldpc_b200_ecc_close",
+    "ldpc_b200_ecc_name", "ldpc_b200_ecc_message_length", "ldpc_b200_ecc_codeword_length",
+    "ldpc_b200_ecc_unpunctured_length", "ldpc_b200_ecc_max_iters", "ldpc_b200_ecc_encode", "ldpc_b200_ecc_decode",
+    "ldpc_b200_ecc_run", "ldpc_b200_ber_line", "ldpc_b200_ecc_encode_device",
+]
+ENOMATCH, ENOENT = -6, -7
+
+
 class Counters(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("frame_errors", C.c_uint64), ("bit_errors", C.c_uint64),
                 ("sum_iters", C.c_uint64), ("unconverged", C.c_uint64), ("kernel_ms", C.c_double)]
@@ -90,6 +100,27 @@ def load():
     L.ldpc_b200_decoder_stream.argtypes = [vp]
     L.ldpc_b200_decoder_stream.restype = vp
     L.ldpc_b200_philox4x32.argtypes = [vp, vp, vp]
+    # host layer (include/ldpc_b200_ecc.h)
+    cs = C.c_char_p
+    L.ldpc_b200_matrix_load.argtypes = [cs, cs, C.POINTER(vp)]
+    L.ldpc_b200_matrix_parse.argtypes = [cs, cs, C.POINTER(vp)]
+    L.ldpc_b200_matrix_destroy.argtypes = [vp]
+    L.ldpc_b200_matrix_destroy.restype = None
+    L.ldpc_b200_matrix_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_int64), C.POINTER(i32)]
+    L.ldpc_b200_matrix_csr.argtypes = [vp, vp, vp]
+    L.ldpc_b200_matrix_qc_shifts.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp]
+    L.ldpc_b200_ecc_open.argtypes = [cs, cs, i32, C.POINTER(vp)]
+    L.ldpc_b200_ecc_close.argtypes = [vp]
+    L.ldpc_b200_ecc_close.restype = None
+    L.ldpc_b200_ecc_name.argtypes = [vp]
+    L.ldpc_b200_ecc_name.restype = cs
+    for fn in ("message_length", "codeword_length", "unpunctured_length", "max_iters"):
+        getattr(L, "ldpc_b200_ecc_" + fn).argtypes = [vp]
+    L.ldpc_b200_ecc_encode.argtypes = [vp, vp, vp]
+    L.ldpc_b200_ecc_decode.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.ldpc_b200_ecc_run.argtypes = [vp, f64, u64, u64, u64, i32, C.POINTER(Counters)]
+    L.ldpc_b200_ber_line.argtypes = [cs, i32, f64, cs, f64, u64, u64, i32]
+    L.ldpc_b200_ecc_encode_device.argtypes = [vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -291,3 +322,112 @@ def unpack_bits(packed, N):
     packed = np.ascontiguousarray(packed, dtype=np.uint32)
     b = np.unpackbits(packed.view(np.uint8).reshape(packed.shape[0], -1), axis=1, bitorder="little")
     return b[:, :N]
+
+
+class HostMatrix:
+    """A matrix file read by the C++ loader (ldpc_b200_matrix_*): Loader.hs / QuasiCyclic.hs / Alist.hs / Matlab.hs."""
+
+    def __init__(self, handle):
+        self.h = handle
+        r, c, sz = C.c_int(), C.c_int(), C.c_int()
+        ones = C.c_int64()
+        check(load().ldpc_b200_matrix_info(self.h, C.byref(r), C.byref(c), C.byref(ones), C.byref(sz)))
+        self.rows, self.cols, self.ones, self.sz = r.value, c.value, ones.value, sz.value
+
+    @classmethod
+    def load(cls, codes_root, path_noext):
+        h = C.c_void_p()
+        check(load().ldpc_b200_matrix_load(codes_root.encode(), path_noext.encode(), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def parse(cls, kind, text):
+        h = C.c_void_p()
+        check(load().ldpc_b200_matrix_parse(kind.encode(), text.encode(), C.byref(h)))
+        return cls(h.value)
+
+    def csr(self):
+        rp = np.zeros(self.rows + 1, dtype=np.int32)
+        ci = np.zeros(max(self.ones, 1), dtype=np.int32)
+        check(load().ldpc_b200_matrix_csr(self.h, rp.ctypes.data, ci.ctypes.data))
+        return rp, ci[:self.ones]
+
+    def qc_shifts(self):
+        br, bc = C.c_int(), C.c_int()
+        check(load().ldpc_b200_matrix_qc_shifts(self.h, C.byref(br), C.byref(bc), None))
+        sh = np.zeros(br.value * bc.value, dtype=np.int32)
+        check(load().ldpc_b200_matrix_qc_shifts(self.h, C.byref(br), C.byref(bc), sh.ctypes.data))
+        return sh.reshape(br.value, bc.value)
+
+    def close(self):
+        if self.h:
+            load().ldpc_b200_matrix_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ecc:
+    """The ECC record of mkLDPC (Utils.hs:59-75) as built by the C++ host layer (ldpc_b200_ecc_*)."""
+
+    def __init__(self, codes_root, name, max_batch=1024):
+        h = C.c_void_p()
+        rc = load().ldpc_b200_ecc_open(codes_root.encode(), name.encode(), max_batch, C.byref(h))
+        check(rc)
+        self.h = h.value
+        L = load()
+        self.name = L.ldpc_b200_ecc_name(self.h).decode()
+        self.message_length = L.ldpc_b200_ecc_message_length(self.h)
+        self.codeword_length = L.ldpc_b200_ecc_codeword_length(self.h)
+        self.unpunctured_length = L.ldpc_b200_ecc_unpunctured_length(self.h)
+        self.max_iters = L.ldpc_b200_ecc_max_iters(self.h)
+
+    def encode(self, msg):
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        assert msg.shape == (self.message_length,)
+        cw = np.zeros(self.codeword_length, dtype=np.uint8)
+        check(load().ldpc_b200_ecc_encode(self.h, msg.ctypes.data, cw.ctypes.data))
+        return cw
+
+    def decode_batch(self, rx):
+        rx = np.ascontiguousarray(rx, dtype=np.float64)
+        if rx.ndim == 1:
+            rx = rx[None, :]
+        F, rl = rx.shape
+        out = np.zeros((F, self.message_length), dtype=np.uint8)
+        flags = np.zeros(F, dtype=np.uint8)
+        check(load().ldpc_b200_ecc_decode(self.h, F, rx.ctypes.data, rl, out.ctypes.data, flags.ctypes.data))
+        return out, flags
+
+    def decode(self, rx):
+        out, flags = self.decode_batch(rx)
+        return out[0], bool(flags[0])
+
+    def run(self, ebn0_db, n_frames, seed=1, first_frame=0, random_messages=False):
+        c = Counters()
+        check(load().ldpc_b200_ecc_run(self.h, ebn0_db, seed, first_frame, n_frames, 1 if random_messages else 0, C.byref(c)))
+        return c.as_dict()
+
+    def encode_device(self, d_msg, d_cw, n_frames):
+        check(load().ldpc_b200_ecc_encode_device(self.h, n_frames, d_msg, d_cw))
+
+    def close(self):
+        if self.h:
+            load().ldpc_b200_ecc_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ber_line(seconds, name, ebn0_db, frames, bit_errors, message_length):
+    buf = C.create_string_buffer(512)
+    load().ldpc_b200_ber_line(buf, 512, seconds, name.encode(), ebn0_db, frames, bit_errors, message_length)
+    return buf.value.decode()

@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    txt = open(os.path.join(ROOT, "include", "ldpc_b200.h")).read()
+def _declared(header="ldpc_b200.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(ldpc_b200_[a-z0-9_]+)\s*\(", txt)))
 
@@ -23,6 +23,11 @@ def test_header_symbols_exported():
         assert hasattr(L, n), "missing export " + n
     assert sorted(lib.EXPORTS) == names
     assert L.ldpc_b200_abi_version() == 1
+    ecc_names = _declared("ldpc_b200_ecc.h")
+    assert len(ecc_names) >= 18
+    for n in ecc_names:
+        assert hasattr(L, n), "missing export " + n
+    assert sorted(lib.ECC_EXPORTS) == ecc_names
 
 
 def test_no_cpu_fallback_without_device():

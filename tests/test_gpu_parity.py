@@ -380,3 +380,56 @@ def test_resident_spa_fp32_vs_oracle(code_name, gpu_lib, dcodes, builtin_codes, 
     d64 = gpu_lib.Decoder(dcodes[code_name], "spa", "fp64", max_batch=8)
     assert d64.engine() == gpu_lib.ENGINE_STREAM
     dec.close(); d64.close()
+
+
+def test_device_encoder_and_tester_point(gpu_lib, builtin_codes):
+    """Device encoder == host encoder (Fast/Encoder.hs:41-63 / Orig.hs:25-26); a tester point with random messages is
+    statistically the same as with the all-zero codeword (linear code, symmetric channel and decoder)."""
+    from ecc_ldpc_b200 import ecc
+    rng = np.random.default_rng(21)
+    for nm, code_name in (("ldpc/b200-minsum/jpl.1024.4.5/20/4/5", "jpl.1024.4.5"), ("ldpc/b200-minsum/jpl.4096.4.5/20/4/5", "jpl.4096.4.5"),
+                          ("ldpc/b200-spa/moon.7.13/20", "moon.7.13")):
+        (e,) = ecc.match(nm, max_batch=512)
+        code = builtin_codes[code_name]
+        F, K, N = 37, code.K, code.N
+        msgs = rng.integers(0, 2, (F, K)).astype(np.uint8)
+        Wk, Wn = (K + 31) // 32, (N + 31) // 32
+        pad = np.zeros((F, Wk * 32), dtype=np.uint8); pad[:, :K] = msgs
+        packed = np.packbits(pad, axis=1, bitorder="little").view(np.uint32)
+        d_msg = gpu_lib.DeviceBuffer(packed.nbytes).upload(packed)
+        d_cw = gpu_lib.DeviceBuffer(F * Wn * 4)
+        e.run(3.0, 1)                                     # creates the device side
+        e.encode_device(d_msg.ptr, d_cw.ptr, F)
+        import ctypes
+        cw = gpu_lib.unpack_bits(d_cw.download(np.uint32, (F, Wn)), N)
+        for f in range(F):
+            want = e.encode(msgs[f])
+            assert np.array_equal(cw[f, :e.codeword_length], want)
+            assert not cw[f, e.codeword_length:].any()
+        e.close()
+    (e,) = ecc.match("ldpc/b200-minsum/jpl.1024.4.5/20/4/5", max_batch=4096)
+    a = e.run(3.3, 8192, seed=3, random_messages=False)
+    b = e.run(3.3, 8192, seed=3, random_messages=True)
+    assert a["frames"] == b["frames"] == 8192
+    fa, fb = a["frame_errors"] / 8192, b["frame_errors"] / 8192
+    assert 0.02 < fa < 0.9
+    assert abs(fa - fb) < 5 * np.sqrt(fa * (1 - fa) / 8192 * 2)          # same FER within 5 sigma
+    assert abs(a["sum_iters"] - b["sum_iters"]) / a["sum_iters"] < 0.03
+    e.close()
+
+
+def test_tester_cli(gpu_lib, tmp_path):
+    """ldpc_b200_tester: the `ecc-ldpc <EbN0...> <code-name...> -m<N>` command line (main/Main.hs:38-48, NOTES.txt:2-3)."""
+    import subprocess
+    from ecc_ldpc_b200 import codes, lib
+    exe = os.path.join(os.path.dirname(lib.SO_PATH), "ldpc_b200_tester")
+    out = subprocess.run([exe, "--codes", codes.builtin_codes_dir(), "0.0", "4.5", "ldpc/b200-minsum/jpl.1024.4.5/20", "bpsk", "-m256"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 2 and "no code matches bpsk" in out.stderr
+    t = lines[0].split()
+    # 0 dB at the default rate 8/11: nothing converges -> the fallback gives the uncoded BER of NOTES.txt:3 (1.14e-1 +-1 %)
+    assert t[1] == "ldpc/b200-minsum/jpl.1024.4.5/20/8/11" and t[2] == "0.0" and t[3] == "256"
+    assert abs(int(t[4]) / (256 * 1024) - 0.1139) < 0.004
+    assert int(lines[1].split()[4]) < int(t[4]) / 20

@@ -188,9 +188,81 @@ def test_uncoded_ber_identity(builtin_codes):
 def test_code_name_grammar():
     """Utils.hs:100-108: ldpc/<decoder>/<matrix>/<max-rounds>[/<num>/<den>]; anything else matches nothing."""
     from ecc_ldpc_b200 import ecc
-    assert ecc.parse_name("ldpc/b200-minsum/jpl.4096.4.5/20/4/5") == ("b200-minsum", "jpl.4096.4.5", 20, (4, 5))
-    assert ecc.parse_name("ldpc/b200-spa/moon.7.13/200") == ("b200-spa", "moon.7.13", 200, None)
+    (e,) = ecc.match("ldpc/b200-minsum/jpl.4096.4.5/20/4/5")
+    assert (e.name, e.message_length, e.codeword_length, e.unpunctured_length, e.max_iters) == \
+        ("ldpc/b200-minsum/jpl.4096.4.5/20/4/5", 4096, 5120, 5632, 20)
+    (m,) = ecc.match("ldpc/b200-spa/moon.7.13/200")
+    assert (m.name, m.message_length, m.codeword_length) == ("ldpc/b200-spa/moon.7.13/200/7/20", 7, 20)   # default rate K/N
+    (j,) = ecc.match("ldpc/b200-minsum/jpl.1024.4.5/20")
+    assert j.name == "ldpc/b200-minsum/jpl.1024.4.5/20/8/11" and j.codeword_length == 1408          # 1024/1408 reduced
     for bad in ("ldpc/reference/moon.7.13/20", "ldpc/b200-minsum/moon.7.13/x", "ldpc/b200-minsum/moon.7.13",
-                "bpsk", "ldpc/b200-minsum/moon.7.13/20/4", "ldpc/b200-minsum/moon.7.13/20/a/5"):
-        assert ecc.parse_name(bad) is None
+                "bpsk", "ldpc/b200-minsum/moon.7.13/20/4", "ldpc/b200-minsum/moon.7.13/20/a/5", ""):
         assert ecc.match(bad) == []
+    from ecc_ldpc_b200 import lib
+    with pytest.raises(lib.LdpcError) as ei:
+        ecc.match("ldpc/b200-minsum/no.such.code/20")
+    assert ei.value.code == lib.ENOENT and "can not find any matrix files" in str(ei.value)
+
+
+def test_cpp_loader_reads_reference_formats(builtin_codes, tmp_path):
+    """The C++ readers (Loader.hs / QuasiCyclic.hs / Alist.hs / Matlab.hs semantics) against the JSON fixtures, through
+    files written in the reference's formats; plus the reference's own files when the checkout is present."""
+    from ecc_ldpc_b200 import codes, lib
+    root = codes.write_reference_dir(str(tmp_path))
+    roots = [root] + (["/root/reference/codes"] if os.path.isdir("/root/reference/codes") else [])
+    for r in roots:
+        for name in ("moon.7.13", "jpl.1024.4.5", "jpl.4096.4.5"):
+            b = builtin_codes[name]
+            H = lib.HostMatrix.load(r, name + "/H")
+            G = lib.HostMatrix.load(r, name + "/G")
+            assert (H.rows, H.cols, H.ones) == (b.M, b.N, b.E) and (G.rows, G.cols) == (b.K, b.N - b.K)
+            rp, ci = H.csr()
+            assert np.array_equal(rp, b.row_ptr) and np.array_equal(ci, b.col_idx)
+            grp, gci = G.csr()
+            assert np.array_equal(grp, b.g_row_ptr) and np.array_equal(gci, b.g_col_idx)
+            if b.is_qc:
+                assert H.sz == b.sz and np.array_equal(H.qc_shifts(), b.shifts)
+                with pytest.raises(lib.LdpcError):
+                    G.qc_shifts()                     # dense circulants: "non-powers of two" (Arraylet.hs:72-79)
+    # search order q > alist > m (Loader.hs:58-62), and the 0/1 matrix format
+    d = tmp_path / "tiny"
+    d.mkdir()
+    (d / "H.m").write_text("1 1 0\n0 1 1\n")
+    m = lib.HostMatrix.load(str(tmp_path), "tiny/H")
+    assert (m.rows, m.cols, m.ones) == (2, 3, 4) and m.csr()[1].tolist() == [0, 1, 1, 2]
+    (d / "H.alist").write_text("2 3\n2 2\n2 1\n1 1 1\n1 3\n2\n1\n2\n1\n")
+    a = lib.HostMatrix.load(str(tmp_path), "tiny/H")
+    assert a.ones == 3 and a.csr()[1].tolist() == [0, 2, 1]
+    (d / "H.q").write_text("2\n1 2 0\n")
+    q = lib.HostMatrix.load(str(tmp_path), "tiny/H")
+    assert (q.rows, q.cols, q.sz) == (2, 6, 2) and q.csr()[1].tolist() == [0, 3, 1, 2] and q.qc_shifts().tolist() == [[0, 1, -1]]
+    with pytest.raises(lib.LdpcError):
+        lib.HostMatrix.parse("m", "1 2\n")
+    with pytest.raises(lib.LdpcError):
+        lib.HostMatrix.parse("q", "4\n1 2\n1\n")
+
+
+def test_cpp_encoder_matches_oracle(builtin_codes):
+    """ldpc_b200_ecc_encode (Fast/Encoder.hs:41-63 word multiply; Orig.hs:25-26 for alist G) == the oracle's dense v*G,
+    and every codeword satisfies H."""
+    from ecc_ldpc_b200 import ecc
+    from oracle import oracle
+    rng = np.random.default_rng(2)
+    for nm, code_name in (("ldpc/b200-minsum/moon.7.13/20", "moon.7.13"), ("ldpc/b200-minsum/jpl.1024.4.5/20/4/5", "jpl.1024.4.5"),
+                          ("ldpc/b200-minsum/jpl.4096.4.5/20", "jpl.4096.4.5")):
+        (e,) = ecc.match(nm)
+        code = builtin_codes[code_name]
+        for t in range(3):
+            msg = rng.integers(0, 2, code.K).astype(np.uint8)
+            cw = e.encode(msg)
+            assert np.array_equal(cw, oracle.encode(code, msg, e.codeword_length))
+            if e.codeword_length == code.N:
+                assert not ((code.dense().astype(np.int64) @ cw) % 2).any()
+        e.close()
+
+
+def test_ber_line_format():
+    """NOTES.txt:3 `39.70 ldpc/model/jpl.1K/200 0.0 256 29891 1.14e-1 +1% -1% 95%`."""
+    from ecc_ldpc_b200 import lib
+    line = lib.ber_line(39.70, "ldpc/model/jpl.1K/200", 0.0, 256, 29891, 1024)
+    assert line == "39.70 ldpc/model/jpl.1K/200 0.0 256 29891 1.14e-1 +1% -1% 95%"
