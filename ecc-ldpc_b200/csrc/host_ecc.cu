@@ -535,6 +535,12 @@ extern "C" int ldpc_b200_ecc_encode_device(ldpc_b200_ecc_t *e, int n_frames, con
     return 0;
 }
 
+extern "C" int ldpc_b200_ecc_sync(ldpc_b200_ecc_t *e)
+{
+    if (!e) { set_error("ecc_sync: null"); return LDPC_B200_EINVAL; }
+    return e->dec ? ldpc_b200_decoder_sync(e->dec) : 0;
+}
+
 extern "C" int ldpc_b200_ecc_run(ldpc_b200_ecc_t *e, double ebn0_db, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
                                  int random_messages, ldpc_b200_counters_t *out)
 {

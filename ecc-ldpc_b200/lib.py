@@ -37,7 +37,7 @@ ECC_EXPORTS = [
     "ldpc_b200_matrix_csr", "ldpc_b200_matrix_qc_shifts", "ldpc_b200_ecc_open", "ldpc_b200_ecc_close",
     "ldpc_b200_ecc_name", "ldpc_b200_ecc_message_length", "ldpc_b200_ecc_codeword_length",
     "ldpc_b200_ecc_unpunctured_length", "ldpc_b200_ecc_max_iters", "ldpc_b200_ecc_encode", "ldpc_b200_ecc_decode",
-    "ldpc_b200_ecc_run", "ldpc_b200_ber_line", "ldpc_b200_ecc_encode_device",
+    "ldpc_b200_ecc_run", "ldpc_b200_ber_line", "ldpc_b200_ecc_encode_device", "ldpc_b200_ecc_sync",
 ]
 ENOMATCH, ENOENT = -6, -7
 
@@ -121,6 +121,7 @@ def load():
     L.ldpc_b200_ecc_run.argtypes = [vp, f64, u64, u64, u64, i32, C.POINTER(Counters)]
     L.ldpc_b200_ber_line.argtypes = [cs, i32, f64, cs, f64, u64, u64, i32]
     L.ldpc_b200_ecc_encode_device.argtypes = [vp, i32, vp, vp]
+    L.ldpc_b200_ecc_sync.argtypes = [vp]
     _lib = L
     return L
 
@@ -414,6 +415,9 @@ class Ecc:
 
     def encode_device(self, d_msg, d_cw, n_frames):
         check(load().ldpc_b200_ecc_encode_device(self.h, n_frames, d_msg, d_cw))
+
+    def sync(self):
+        check(load().ldpc_b200_ecc_sync(self.h))
 
     def close(self):
         if self.h:

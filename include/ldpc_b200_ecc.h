@@ -80,6 +80,8 @@ int ldpc_b200_ber_line(char *buf, int buf_len, double seconds, const char *name,
 /* Device encoder on packed words: d_msg n_frames x ceil(K/32) -> d_cw n_frames x ceil(N/32) with the
  * parity bits beyond codeword_length cleared. Asynchronous on the ECC's decoder stream. */
 int ldpc_b200_ecc_encode_device(ldpc_b200_ecc_t *e, int n_frames, const uint32_t *d_msg_packed, uint32_t *d_cw_packed);
+/* Wait for the asynchronous work of this ECC's decoder stream. */
+int ldpc_b200_ecc_sync(ldpc_b200_ecc_t *e);
 
 #ifdef __cplusplus
 }

@@ -400,7 +400,7 @@ def test_device_encoder_and_tester_point(gpu_lib, builtin_codes):
         d_cw = gpu_lib.DeviceBuffer(F * Wn * 4)
         e.run(3.0, 1)                                     # creates the device side
         e.encode_device(d_msg.ptr, d_cw.ptr, F)
-        import ctypes
+        e.sync()
         cw = gpu_lib.unpack_bits(d_cw.download(np.uint32, (F, Wn)), N)
         for f in range(F):
             want = e.encode(msgs[f])
