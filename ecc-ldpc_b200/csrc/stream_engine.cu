@@ -19,6 +19,8 @@
 
 namespace ldpc {
 
+#include "spa_fp32.cuh"
+
 static constexpr int TPB = 128;   // threads per block along the frame axis
 
 template <typename T> struct Num;
@@ -132,7 +134,31 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
     if (f >= F) return;
     if (skip_done && state[f]) return;
     int b = g.row_ptr[m], d = g.row_ptr[m + 1] - b;
-    if (ALGO == LDPC_B200_ALGO_SPA) {
+    if (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4) {
+        // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) combined leave-one-out by
+        // prefix / suffix, magnitude 2 atanh(1 - c) capped at the reference's clamp, sign = -(product of the other signs).
+        // The literal tanh-product below saturates in fp32 and shows an error floor the fp64 reference does not have.
+        float c[MAXD], pre[MAXD];
+        uint32_t sgn = 0;
+        float run = 0.0f;                                  // identity: c = 0 <=> tanh = 1
+        for (int k = 0; k < d; k++) {
+            float x = -(float)Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            sgn ^= __float_as_uint(x);
+            c[k] = spa_compl(x);
+            pre[k] = run;
+            run = fmaf(-run, c[k], run + c[k]);
+            ne[(size_t)(b + k) * Bp + f] = (T)x;           // keep x for the sign of the edge
+        }
+        sgn = ~sgn;
+        float suf = 0.0f;
+        for (int k = d - 1; k >= 0; k--) {
+            float others = fmaf(-pre[k], suf, pre[k] + suf);
+            float x = (float)ne[(size_t)(b + k) * Bp + f];
+            float v = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(x)) & 0x80000000u));
+            ne[(size_t)(b + k) * Bp + f] = (T)v;
+            suf = fmaf(-suf, c[k], suf + c[k]);
+        }
+    } else if (ALGO == LDPC_B200_ALGO_SPA) {
         // Orig.hs:86-91: tanh(-((lam_j - ne[m,j]) / 2)) per edge, leave-one-out LEFT fold of (*) from 1.
         T t[MAXD];
         for (int k = 0; k < d; k++) {
