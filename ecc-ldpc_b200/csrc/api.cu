@@ -201,7 +201,7 @@ int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_
     c->row_ptr.assign(row_ptr, row_ptr + M + 1);
     c->col_idx.assign(col_idx, col_idx + row_ptr[M]);
     finish_code(c);
-    c->device = g_device;
+    LDPC_CUDA(cudaGetDevice(&c->device));        // the code lives on the CURRENT device (multi-GPU hosts switch devices)
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }
     *out = c;
@@ -232,7 +232,7 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
             c->row_ptr[m + 1] = (int32_t)c->col_idx.size();
         }
     finish_code(c);
-    c->device = g_device;
+    LDPC_CUDA(cudaGetDevice(&c->device));
     c->resident_kind = resident_kind_for(c);
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }

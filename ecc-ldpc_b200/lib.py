@@ -26,7 +26,8 @@ EXPORTS = [
     "ldpc_b200_decoder_set_engine", "ldpc_b200_decoder_engine", "ldpc_b200_decoder_destroy",
     "ldpc_b200_decode", "ldpc_b200_decode_f32", "ldpc_b200_decode_trace", "ldpc_b200_decode_device",
     "ldpc_b200_decoder_sync", "ldpc_b200_decoder_last_timing", "ldpc_b200_generate_llr",
-    "ldpc_b200_simulate", "ldpc_b200_simulate_device", "ldpc_b200_count_errors", "ldpc_b200_malloc", "ldpc_b200_free",
+    "ldpc_b200_simulate", "ldpc_b200_simulate_device", "ldpc_b200_simulate_multi", "ldpc_b200_simulate_multi_release",
+    "ldpc_b200_count_errors", "ldpc_b200_malloc", "ldpc_b200_free",
     "ldpc_b200_malloc_host", "ldpc_b200_free_host", "ldpc_b200_memcpy_h2d", "ldpc_b200_memcpy_d2h",
     "ldpc_b200_memset", "ldpc_b200_decoder_stream", "ldpc_b200_philox4x32",
 ]
@@ -90,6 +91,8 @@ def load():
     L.ldpc_b200_simulate.argtypes = [vp, i32, i32, f64, i32, i32, u64, u64, u64, C.POINTER(Counters)]
     L.ldpc_b200_simulate_device.argtypes = [vp, i32, i32, f64, i32, i32, u64, u64, u64, vp]
     L.ldpc_b200_count_errors.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.ldpc_b200_simulate_multi.argtypes = [vp, i32, i32, i32, i32, i32, i32, f64, i32, i32, u64, u64, u64, C.POINTER(Counters)]
+    L.ldpc_b200_simulate_multi_release.restype = None
     L.ldpc_b200_malloc.argtypes = [C.POINTER(vp), u64]
     L.ldpc_b200_free.argtypes = [vp]
     L.ldpc_b200_malloc_host.argtypes = [C.POINTER(vp), u64]
@@ -316,6 +319,15 @@ class Decoder:
             self.close()
         except Exception:
             pass
+
+
+def simulate_multi(dcode, n_gpus, algo, precision, max_batch, max_iters, ebn0_db, k_info, n_tx, seed, first_frame, n_frames,
+                   early_exit=True):
+    """ldpc_b200_simulate_multi: one process, n_gpus devices, NCCL all-reduce of the counters."""
+    c = Counters()
+    check(load().ldpc_b200_simulate_multi(dcode.h, n_gpus, ALGO[algo], PREC[precision], max_batch, max_iters, 1 if early_exit else 0,
+                                          ebn0_db, k_info, n_tx, seed, first_frame, n_frames, C.byref(c)))
+    return c.as_dict()
 
 
 def unpack_bits(packed, N):

@@ -135,6 +135,15 @@ int ldpc_b200_simulate(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, 
 int ldpc_b200_simulate_device(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, double ebn0_db, int k_info,
                               int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames, uint64_t *d_counters);
 
+/* Single-process multi-GPU form (one host process driving n_gpus devices 0..n_gpus-1, e.g. the Haskell tester): H is
+ * replicated, GPU g simulates a contiguous share of [first_frame, first_frame+n_frames), and the five counters are summed
+ * with one NCCL all-reduce (libnccl.so.2 is loaded at run time). Results are independent of n_gpus. Counters are ADDED to
+ * *out; kernel_ms is the maximum over the GPUs. The replicas are cached until ldpc_b200_simulate_multi_release(). */
+int ldpc_b200_simulate_multi(const ldpc_b200_code_t *code, int n_gpus, int algo, int precision, int max_batch, int max_iters,
+                             int early_exit, double ebn0_db, int k_info, int n_tx, uint64_t seed, uint64_t first_frame,
+                             uint64_t n_frames, ldpc_b200_counters_t *out);
+void ldpc_b200_simulate_multi_release(void);
+
 /* Error counting for device-resident decisions: adds {frames, frame errors, bit errors over the first k_info bits,
  * sum of iterations, unconverged} of n_frames frames to d_counters (5 x uint64, device). d_ref_packed = transmitted
  * codewords (n_frames x ceil(N/32)) or NULL for the all-zero codeword. Asynchronous on the decoder's stream. */

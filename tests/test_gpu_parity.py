@@ -433,3 +433,22 @@ def test_tester_cli(gpu_lib, tmp_path):
     assert t[1] == "ldpc/b200-minsum/jpl.1024.4.5/20/8/11" and t[2] == "0.0" and t[3] == "256"
     assert abs(int(t[4]) / (256 * 1024) - 0.1139) < 0.004
     assert int(lines[1].split()[4]) < int(t[4]) / 20
+
+
+def test_simulate_multi_single_process(gpu_lib, dcodes, builtin_codes):
+    """ldpc_b200_simulate_multi: results do not depend on the number of GPUs (frame-index keyed Philox, contiguous
+    shards, NCCL sum of the counters). With one visible GPU only the n_gpus = 1 leg runs."""
+    code = builtin_codes["jpl.1024.4.5"]
+    dec = gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp32", max_batch=512)
+    want = dec.simulate(20, 3.4, code.K, 1280, 9, 100, 3001)
+    dec.close()
+    n_dev = gpu_lib.load().ldpc_b200_device_count()
+    for n in (1, 2, 4, 8):
+        if n > n_dev:
+            break
+        got = gpu_lib.simulate_multi(dcodes["jpl.1024.4.5"], n, "min", "fp32", 512, 20, 3.4, code.K, 1280, 9, 100, 3001)
+        for k in ("frames", "frame_errors", "bit_errors", "sum_iters", "unconverged"):
+            assert got[k] == want[k], (n, k)
+    gpu_lib.load().ldpc_b200_simulate_multi_release()
+    with pytest.raises(gpu_lib.LdpcError):
+        gpu_lib.simulate_multi(dcodes["jpl.1024.4.5"], n_dev + 1, "min", "fp32", 512, 20, 3.4, code.K, 1280, 9, 0, 10)
