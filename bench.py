@@ -115,8 +115,39 @@ def reference_arm(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank (and allocate its pinned host buffers) on the NUMA node its GPU hangs off, so that the e2e leg's
+    H2D/D2H copies of 8 ranks do not all cross the socket interconnect. Best effort; returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (e.g. NCCL's version banner) was
+    redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -145,6 +176,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libldpc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -332,7 +364,8 @@ def main():
             "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
                        "frames_per_step_per_gpu": B, "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident"}[dec.engine()],
                        "l2": "inputs larger than L2 (%.0f MB of LLRs per step per GPU)" % (B * code.N * 4 / 1e6),
-                       "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step"},
+                       "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step",
+                       "numa_node_rank0": numa},
             "frames_per_s": fps, "edge_updates_per_s": fps * avg_iters * code.E,
             "gpu_launches": int(sum(launches) / len(launches) + 1) * args.steps,
             "clocks": clocks,
@@ -343,7 +376,7 @@ def main():
             "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
