@@ -314,6 +314,9 @@ __device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t 
     typedef FB<T> F;
     constexpr int BLK = C::SZ * sizeof(T);
     constexpr int NEGL = QcMap<C>::N * sizeof(T);
+    // Two passes: every load of the stage is issued before the first store.  The accesses are volatile asm and keep
+    // their program order, so a fused load-subtract-store per link would serialise the stage on shared-memory latency.
+    T acc[C::BC];
     static_for<C::BC>([&](auto ci) {
         constexpr int c = decltype(ci)::value;
         constexpr int step = C::col_stage[c][Q];          // which link of column c's chain runs in this stage
@@ -321,10 +324,21 @@ __device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t 
             constexpr int r = C::col_row_desc[c][step];
             if constexpr (C::half_of_row[r] == H) {
                 constexpr int k = C::col_k_desc[c][step];
+                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
+                acc[c] = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * BLK>(a);
+            }
+        }
+    });
+    static_for<C::BC>([&](auto ci) {
+        constexpr int c = decltype(ci)::value;
+        constexpr int step = C::col_stage[c][Q];
+        if constexpr (step >= 0) {
+            constexpr int r = C::col_row_desc[c][step];
+            if constexpr (C::half_of_row[r] == H) {
+                constexpr int k = C::col_k_desc[c][step];
                 constexpr int e = QcMap<C>::reg_base(r) + k;
                 uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                T acc = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * BLK>(a);
-                F::template sts<c * BLK>(a, F::sub(acc, ne[e]));
+                F::template sts<c * BLK>(a, F::sub(acc[c], ne[e]));
             }
         }
     });

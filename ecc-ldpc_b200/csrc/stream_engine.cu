@@ -69,7 +69,7 @@ template <typename T>
 __global__ void k_syndrome(DeviceGraph g, const T *__restrict__ lam, const uint8_t *__restrict__ state,
                            uint8_t *__restrict__ unsat, int F, int Bp, int skip_done)
 {
-    int f = blockIdx.x * TPB + threadIdx.x, m = blockIdx.y;
+    int f = blockIdx.y * TPB + threadIdx.x, m = blockIdx.x;       // frame block = slow grid axis: see launch comment
     if (f >= F) return;
     if (skip_done && state[f]) return;
     int p = 0;
@@ -101,7 +101,7 @@ template <typename T>
 __global__ void k_hard(const T *__restrict__ lam, const T *__restrict__ L, const uint8_t *__restrict__ state,
                        const int32_t *__restrict__ iters, uint32_t *__restrict__ bits, int n, int N, int F, int Bp)
 {
-    int f = blockIdx.x * TPB + threadIdx.x, w = blockIdx.y;
+    int f = blockIdx.y * TPB + threadIdx.x, w = blockIdx.x;
     if (f >= F) return;
     uint8_t s = state[f];
     if (s == 0 || iters[f] != n) return;
@@ -128,12 +128,17 @@ __device__ __forceinline__ T atanh_prime(T x)
 // Check-node update, one thread per (check, frame).
 template <typename T, int ALGO, int MAXD>
 __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ ne,
-                     const uint8_t *__restrict__ state, int F, int Bp, int skip_done)
+                     const uint8_t *__restrict__ state, uint8_t *__restrict__ unsat, int F, int Bp, int skip_done)
 {
-    int f = blockIdx.x * TPB + threadIdx.x, m = blockIdx.y;
+    int f = blockIdx.y * TPB + threadIdx.x, m = blockIdx.x;
     if (f >= F) return;
     if (skip_done && state[f]) return;
     int b = g.row_ptr[m], d = g.row_ptr[m + 1] - b;
+    {   // syndrome of the CURRENT posteriors (Orig.hs:73-78) rides on the same gather; k_status reads it after this kernel
+        int par = 0;
+        for (int k = 0; k < d; k++) par ^= (lam[(size_t)g.col_idx[b + k] * Bp + f] > (T)0);
+        if (par) unsat[f] = 1;
+    }
     if (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4) {
         // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) combined leave-one-out by
         // prefix / suffix, magnitude 2 atanh(1 - c) capped at the reference's clamp, sign = -(product of the other signs).
@@ -194,7 +199,7 @@ template <typename T>
 __global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict__ ne, T *__restrict__ lam,
                      const uint8_t *__restrict__ state, int F, int Bp, int skip_done)
 {
-    int f = blockIdx.x * TPB + threadIdx.x, j = blockIdx.y;
+    int f = blockIdx.y * TPB + threadIdx.x, j = blockIdx.x;
     if (f >= F) return;
     if (skip_done && state[f]) return;
     T acc = L[(size_t)j * Bp + f];
@@ -243,11 +248,11 @@ static int launch_cn(ldpc_b200_decoder *d, dim3 grid, int F, int skip_done)
     const DeviceGraph &g = d->code->g;
     StreamBuffers &s = d->sb;
     if (g.max_row_deg <= 8)
-        k_cn<T, ALGO, 8><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+        k_cn<T, ALGO, 8><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
     else if (g.max_row_deg <= 32)
-        k_cn<T, ALGO, 32><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+        k_cn<T, ALGO, 32><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
     else
-        k_cn<T, ALGO, 128><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, F, s.Bp, skip_done);
+        k_cn<T, ALGO, 128><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
     d->launches++;
     return 0;
 }
@@ -276,12 +281,24 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
         else k_load<T, float><<<grid, blk, 0, st>>>((const float *)d_llr, (T *)s.L, (T *)s.lam, N, F, Bp);
         d->launches++;
     }
+    // Grid layout: blockIdx.x = check / variable / word, blockIdx.y = block of 128 frames.  CTAs are dispatched x-fastest,
+    // so all checks of one frame block run back to back and the posterior lines they gather (N x 512 B) stay in L2:
+    // DRAM sees each posterior once per phase, which is what the algorithmic-bytes model assumes.
+    // Per iteration n: k_cn (syndrome of lam_n + new messages) -> k_status -> k_hard -> k_vn.  A frame whose syndrome
+    // turns out to be zero has computed one set of messages it never uses; in exchange there is no separate syndrome pass.
     std::vector<T> tmp;
     for (int n = 0;; n++) {
-        if (M > 0) { k_syndrome<T><<<dim3(fb, M), TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
+        dim3 gcn(M, fb);
+        if (n >= max_iters) {
+            if (M > 0) { k_syndrome<T><<<gcn, TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
+        } else if (M > 0) {
+            // converged frames are skipped via `state` when early exit is on; with early_exit = 0 they keep iterating
+            if (d->algo == LDPC_B200_ALGO_SPA) launch_cn<T, LDPC_B200_ALGO_SPA>(d, gcn, F, skip);
+            else launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, gcn, F, skip);
+        }
         LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));
         k_status<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.unsat, s.iters, s.active, n, max_iters, F);
-        k_hard<T><<<dim3(fb, words_per_frame(N)), TPB, 0, st>>>((const T *)s.lam, (const T *)s.L, s.state, s.iters, d_bits, n, N, F, Bp);
+        k_hard<T><<<dim3(words_per_frame(N), fb), TPB, 0, st>>>((const T *)s.lam, (const T *)s.L, s.state, s.iters, d_bits, n, N, F, Bp);
         d->launches += 2;
         if (n >= max_iters) break;
         if (early_exit) {
@@ -290,10 +307,7 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             LDPC_CUDA(cudaStreamSynchronize(st));
             if (active == 0) break;
         }
-        dim3 gcn(fb, M);
-        if (d->algo == LDPC_B200_ALGO_SPA) launch_cn<T, LDPC_B200_ALGO_SPA>(d, gcn, F, skip);
-        else launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, gcn, F, skip);
-        k_vn<T><<<dim3(fb, N), TPB, 0, st>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, Bp, skip);
+        k_vn<T><<<dim3(N, fb), TPB, 0, st>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, Bp, skip);
         d->launches++;
         if (h_c2v || h_lam) {   // trace of frame 0: column 0 of the frame-minor arrays
             size_t need = (size_t)(E > N ? E : N);
