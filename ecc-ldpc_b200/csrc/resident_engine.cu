@@ -35,6 +35,10 @@
 #ifndef RES_PARTS
 #define RES_PARTS 2
 #endif
+// RES_SPA_LOOPED: sum-product check phase with one shared copy of the big-row arithmetic (see cn_phase_spa_looped)
+#ifndef RES_SPA_LOOPED
+#define RES_SPA_LOOPED 1
+#endif
 
 namespace ldpc {
 
@@ -285,6 +289,117 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ui
     return unsat & F::SIGN;        // non-zero sign bit(s): an unsatisfied check (one bit per packed frame)
 }
 
+// Exclusive compile-time dispatch on a run-time index: a binary tree of (warp-uniform) branches whose leaves call
+// fn(integral_constant<idx>).
+template <int LO, int HI, class Fn>
+__device__ __forceinline__ void dispatch_index(int sel, Fn &&fn)
+{
+    if constexpr (HI - LO == 1) fn(std::integral_constant<int, LO>{});
+    else {
+        constexpr int MID = (LO + HI) / 2;
+        if (sel < MID) dispatch_index<LO, MID>(sel, fn);
+        else dispatch_index<MID, HI>(sel, fn);
+    }
+}
+
+// The "big" rows of a code are those of maximum degree (18 for the AR4JA codes); every part carries the same number.
+template <class C> struct BigRows {
+    static __host__ __device__ constexpr int count(int h)
+    {
+        int n = 0;
+        for (int q = 0; q < C::HR; q++) n += C::row_deg[C::half_rows[h][q]] == C::MAXD;
+        return n;
+    }
+    static __host__ __device__ constexpr int row(int h, int j)
+    {
+        for (int q = 0; q < C::HR; q++)
+            if (C::row_deg[C::half_rows[h][q]] == C::MAXD && j-- == 0) return C::half_rows[h][q];
+        return -1;
+    }
+    static __host__ __device__ constexpr bool uniform()
+    {
+        for (int h = 1; h < C::NP; h++) if (count(h) != count(0)) return false;
+        return true;
+    }
+    static constexpr int NB = count(0);
+};
+
+// Sum-product check phase with ONE copy of the arithmetic of a big row.  Fully unrolled, the sum-product loop body
+// is ~100 KB of SASS (30 instructions per edge, 156 circulants): it does not fit the 32 KB instruction cache and the
+// kernel was fetch-bound (ncu: 43 % of the stall samples `no_instruction`).  Here the per-row code is only what
+// depends on the circulant table -- gather x = ne + mu at the start, the sign/magnitude merge into ne' at the end --
+// selected by a warp-uniform branch tree; the complement / tree / logarithm arithmetic of a degree-MAXD row exists once
+// and is shared by all big rows of all parts.  The small rows (degree 3) stay inline.
+template <class C>
+__device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NEH], uint32_t P, int h)
+{
+    typedef FB<float> F;
+    constexpr int BLK = C::SZ * sizeof(float), D = C::MAXD, NB = BigRows<C>::NB;
+    static_assert(BigRows<C>::uniform(), "parts must carry the same number of maximum-degree rows");
+    uint32_t unsat = 0;
+    dispatch_index<0, C::NP>(h, [&](auto hi) {
+        constexpr int H = decltype(hi)::value;
+        static_for<C::HR>([&](auto qi) {
+            constexpr int r = C::half_rows[H][decltype(qi)::value];
+            constexpr int d = C::row_deg[r];
+            constexpr int base = QcMap<C>::reg_base(r);
+            if constexpr (d != D) {
+                uint32_t par = 0, sgn = 0;
+                static_for<d>([&](auto ki) {
+                    constexpr int k = decltype(ki)::value;
+                    float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                    par ^= F::bits(m);
+                    ne[base + k] = F::add(ne[base + k], m);
+                    sgn ^= F::bits(ne[base + k]);
+                });
+                unsat |= par;
+                sgn = ~sgn;
+                BoxTree<float, 0, d, OpCompl> tree;
+                tree.build([&](auto ki) { return spa_compl(ne[base + decltype(ki)::value]); });
+                tree.down_root([&](auto ki, float others) {
+                    constexpr int k = decltype(ki)::value;
+                    ne[base + k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                });
+            }
+        });
+    });
+#pragma unroll 1
+    for (int j = 0; j < NB; j++) {
+        float xs[D];
+        uint32_t par = 0;
+        const int sel = h * NB + j;
+        dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
+            constexpr int idx = decltype(ci)::value;
+            constexpr int r = BigRows<C>::row(idx / NB, idx % NB);
+            constexpr int base = QcMap<C>::reg_base(r);
+            static_for<D>([&](auto ki) {
+                constexpr int k = decltype(ki)::value;
+                float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                par ^= F::bits(m);
+                xs[k] = F::add(ne[base + k], m);                  // x = ne + mu   (Orig.hs:84)
+            });
+        });
+        unsat |= par;
+        // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form
+        uint32_t sgn = 0;
+        static_for<D>([&](auto ki) { sgn ^= __float_as_uint(xs[decltype(ki)::value]); });
+        sgn = ~sgn;                                               // leading minus times the product of ALL signs
+        BoxTree<float, 0, D, OpCompl> tree;
+        tree.build([&](auto ki) { return spa_compl(xs[decltype(ki)::value]); });
+        tree.down_root([&](auto ki, float others) {
+            constexpr int k = decltype(ki)::value;
+            // own sign removed from the product: sgn ^ sign(x_k); the magnitude is >= 0 so its sign bit is free
+            xs[k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(xs[k])) & 0x80000000u));
+        });
+        dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
+            constexpr int idx = decltype(ci)::value;
+            constexpr int base = QcMap<C>::reg_base(BigRows<C>::row(idx / NB, idx % NB));
+            static_for<D>([&](auto ki) { ne[base + decltype(ki)::value] = xs[decltype(ki)::value]; });
+        });
+    }
+    return unsat & F::SIGN;
+}
+
 // Syndrome only (used for the test after the last iteration).
 template <class C, typename T, int H>
 __device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
@@ -365,9 +480,11 @@ struct FrameCounters {
 
 // Decode of one frame by the threads of part H (the iteration loop is instantiated per part so that no dispatch
 // happens inside it; all parts execute the same sequence of named barriers).
+// H >= 0: instance for part H.  H = -1: one instance for all parts with the part h as a run-time value (the sum-product
+// form, whose big-row arithmetic is shared: cn_phase_spa_looped); table-dependent phases branch on h (warp-uniform).
 template <class C, typename T, int H, int ALGO>
 __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned int f, const T *mu, const T *negL, uint32_t P,
-                                             int bar, int tf, int lane, FrameCounters &cnt)
+                                             int bar, int tf, int lane, FrameCounters &cnt, int h = H)
 {
     typedef QcMap<C> Mp;
     constexpr int N = Mp::N, TPF = C::NP * C::SZ, WPF = TPF / 32, W = N / 32;
@@ -380,7 +497,15 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
     for (int n = 0;; n++) {
         bool finished_now = false, conv = false;
         if (!(done && n == p.max_iters)) {
-            bool unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO>(ne, P)) != 0;
+            bool unsat;
+            if constexpr (H >= 0) {
+                unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO>(ne, P)) != 0;
+            } else {
+                typename FB<T>::B u = 0;
+                if (n == p.max_iters) dispatch_index<0, C::NP>(h, [&](auto hi) { u = synd_phase<C, T, decltype(hi)::value>(P); });
+                else u = cn_phase_spa_looped<C>(ne, P, h);
+                unsat = u != 0;
+            }
             bool any = bar_or(bar, TPF, unsat);
             if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
         }
@@ -414,7 +539,8 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
 
         // ---- variable phase ----
         static_for<C::MAXCD>([&](auto qi) {
-            vn_stage<C, T, H, decltype(qi)::value>(ne, P);
+            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value>(ne, P);
+            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value>(ne, P); });
             bar_sync(bar, TPF);
         });
     }
@@ -460,7 +586,9 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
         }
         bar_sync(bar, TPF);
 
-        if constexpr (C::NP == 2) {
+        if constexpr (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4 && RES_SPA_LOOPED) {
+            decode_frame<C, T, -1, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt, h);
+        } else if constexpr (C::NP == 2) {
             if (h == 0) decode_frame<C, T, 0, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
             else decode_frame<C, T, 1, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
         } else {
