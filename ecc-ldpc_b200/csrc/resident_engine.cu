@@ -244,6 +244,11 @@ template <typename T, int LO, class Op> struct BoxTree<T, LO, LO + 1, Op> {
 
 #include "spa_fp32.cuh"
 struct OpCompl { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-a, b, a + b); } };
+// the same on magnitudes (|.| is an operand modifier of FADD / FFMA): leaves may carry a payload in their sign bit
+struct OpComplAbs { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-fabsf(a), fabsf(b), fabsf(a) + fabsf(b)); } };
+// lg2((2 - c) / c) = 2 atanh(1 - c) / ln 2 (uncapped), and the reference's ceiling 2 * 18.714973875118524 in the same unit
+__device__ __forceinline__ float spa_mag_lg2(float c) { c = fabsf(c); return mufu_lg2(2.0f - c) - mufu_lg2(c); }
+#define SPA_CAP_LG2 54.0f   // 2 * 18.714973875118524 = ln((2 - 2^-53) / 2^-53) = 54 ln 2 to within 1e-16
 
 // Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
 // checks is unsatisfied by hard(lam).
@@ -380,21 +385,28 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
             });
         });
         unsat |= par;
-        // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form
+        // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form.
+        // The sign of x_k rides in the sign bit of its (non-negative) complement: the tree reads magnitudes through
+        // operand modifiers, so x itself is dead after this point (18 registers less at the widest place).
         uint32_t sgn = 0;
         static_for<D>([&](auto ki) { sgn ^= __float_as_uint(xs[decltype(ki)::value]); });
-        sgn = ~sgn;                                               // leading minus times the product of ALL signs
-        BoxTree<float, 0, D, OpCompl> tree;
-        tree.build([&](auto ki) { return spa_compl(xs[decltype(ki)::value]); });
+        // cap with the sign "leading minus times the product of ALL signs" (still to be multiplied by sign(x_k))
+        const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
+        static_for<D>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            xs[k] = __uint_as_float(__float_as_uint(spa_compl(xs[k])) | (__float_as_uint(xs[k]) & 0x80000000u));
+        });
+        BoxTree<float, 0, D, OpComplAbs> tree;
+        tree.build([&](auto ki) { return xs[decltype(ki)::value]; });
         tree.down_root([&](auto ki, float others) {
             constexpr int k = decltype(ki)::value;
-            // own sign removed from the product: sgn ^ sign(x_k); the magnitude is >= 0 so its sign bit is free
-            xs[k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(xs[k])) & 0x80000000u));
+            // min(|lg2((2-c)/c)|, cap) with sign = sign(cap_s) xor sign(x_k): one LOP3 + one FMNMX.XORSIGN
+            xs[k] = F::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(xs[k]) & 0x80000000u)));
         });
         dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
             constexpr int idx = decltype(ci)::value;
             constexpr int base = QcMap<C>::reg_base(BigRows<C>::row(idx / NB, idx % NB));
-            static_for<D>([&](auto ki) { ne[base + decltype(ki)::value] = xs[decltype(ki)::value]; });
+            static_for<D>([&](auto ki) { ne[base + decltype(ki)::value] = xs[decltype(ki)::value] * 0.69314718055994531f; });
         });
     }
     return unsat & F::SIGN;
