@@ -55,6 +55,32 @@ static int upload_graph(ldpc_b200_code *c)
         LDPC_CUDA(cudaMemcpy(g.col_idx, c->col_idx.data(), sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
         LDPC_CUDA(cudaMemcpy(g.col_edge, c->col_edge.data(), sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
     }
+    // fixed-stride records (see DeviceGraph)
+    const int classes[4] = {4, 8, 18, 32};
+    g.row_ell_d = 0;
+    for (int k = 0; k < 4 && !g.row_ell_d; k++) if (c->max_row_deg <= classes[k]) g.row_ell_d = classes[k];
+    if (g.row_ell_d && c->M > 0) {
+        const int S = g.row_ell_d + 2;
+        std::vector<int32_t> t((size_t)c->M * S, 0);
+        for (int m = 0; m < c->M; m++) {
+            int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
+            t[(size_t)m * S] = b; t[(size_t)m * S + 1] = d;
+            for (int k = 0; k < g.row_ell_d; k++) t[(size_t)m * S + 2 + k] = d > 0 ? c->col_idx[b + (k < d ? k : d - 1)] : 0;
+        }
+        LDPC_CUDA(cudaMalloc(&g.row_ell, sizeof(int32_t) * t.size()));
+        LDPC_CUDA(cudaMemcpy(g.row_ell, t.data(), sizeof(int32_t) * t.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        const int D = DeviceGraph::COL_ELL_D, S = D + 1;
+        std::vector<int32_t> t((size_t)c->N * S, 0);
+        for (int j = 0; j < c->N; j++) {
+            int q0 = c->col_ptr[j], d = c->col_ptr[j + 1] - q0;
+            t[(size_t)j * S] = d;
+            for (int k = 0; k < D; k++) t[(size_t)j * S + 1 + k] = d > 0 ? c->col_edge[q0 + d - 1 - (k < d ? k : d - 1)] : 0;
+        }
+        LDPC_CUDA(cudaMalloc(&g.col_ell, sizeof(int32_t) * t.size()));
+        LDPC_CUDA(cudaMemcpy(g.col_ell, t.data(), sizeof(int32_t) * t.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -244,6 +270,7 @@ void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
 {
     if (!c) return;
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
+    cudaFree(c->g.row_ell); cudaFree(c->g.col_ell);
     delete c;
 }
 

@@ -25,6 +25,14 @@ struct DeviceGraph {
     int32_t *col_idx = nullptr;   // [E]  edge -> variable
     int32_t *col_ptr = nullptr;   // [N+1]
     int32_t *col_edge = nullptr;  // [E]  edges of variable j, ascending check index
+    // Fixed-stride records for the STREAM kernels: one cooperative load per CTA replaces the dependent
+    // row_ptr -> col_idx (col_ptr -> col_edge) chain in front of the bulk loads.
+    //   row_ell [M][row_ell_d + 2] : {first edge b, degree d, col_idx[b .. b+d-1], last column repeated}; null if max_row_deg > 32
+    //   col_ell [N][COL_ELL_D + 1] : {degree d, edges of the variable in DESCENDING check order (the order of the
+    //                                 reference's right fold), first COL_ELL_D of them, last one repeated}
+    int32_t *row_ell = nullptr, *col_ell = nullptr;
+    int row_ell_d = 0;
+    static constexpr int COL_ELL_D = 8;
 };
 
 }  // namespace ldpc

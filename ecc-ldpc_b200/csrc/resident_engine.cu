@@ -43,68 +43,7 @@
 namespace ldpc {
 
 #include "qc_tables.inc"
-
-template <int... Is, class F>
-__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f)
-{
-    (f(std::integral_constant<int, Is>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F &&f)
-{
-    static_for_impl(std::make_integer_sequence<int, N>{}, f);
-}
-
-// Arithmetic with explicit rounding (no FMA contraction), bit access, and shared-memory access by 32-bit shared
-// address + compile-time byte offset (so that the block-column offset rides in the instruction's immediate).
-template <typename T> struct FB;
-template <> struct FB<float> {
-    typedef uint32_t B;
-    static constexpr B SIGN = 0x80000000u;
-    static __device__ __forceinline__ B bits(float x) { return __float_as_uint(x); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    // min' of Min.hs:89 in ONE instruction: FMNMX.XORSIGN = min(|a|,|b|) carrying sign(a) xor sign(b)
-    static __device__ __forceinline__ float box(float a, float b)
-    {
-        float r;
-        asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-        return r;
-    }
-    template <int OFF> static __device__ __forceinline__ float lds(uint32_t addr)
-    {
-        float v;
-        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
-        return v;
-    }
-    template <int OFF> static __device__ __forceinline__ void sts(uint32_t addr, float v)
-    {
-        asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v));
-    }
-};
-template <> struct FB<double> {
-    typedef unsigned long long B;
-    static constexpr B SIGN = 0x8000000000000000ull;
-    static __device__ __forceinline__ B bits(double x) { return (B)__double_as_longlong(x); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double box(double a, double b)
-    {
-        return __longlong_as_double((long long)(bits(fmin(fabs(a), fabs(b))) | ((bits(a) ^ bits(b)) & SIGN)));
-    }
-    template <int OFF> static __device__ __forceinline__ double lds(uint32_t addr)
-    {
-        double v;
-        asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
-        return v;
-    }
-    template <int OFF> static __device__ __forceinline__ void sts(uint32_t addr, double v)
-    {
-        asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v));
-    }
-};
+#include "bp_tree.cuh"
 
 // Two frames per thread, packed as an fp32 pair in one 64-bit register pair.  sm_100 has packed fp32 arithmetic
 // (FADD2 / FMUL2 / FFMA2 on register pairs), 64-bit shared-memory accesses move both frames' words in one
@@ -202,53 +141,11 @@ __device__ __forceinline__ uint32_t rot(uint32_t P)
 template <typename T> __device__ __forceinline__ T minus34() { return (T)-0.75; }
 template <> __device__ __forceinline__ f2 minus34<f2>() { return mk_f2(-0.75f, -0.75f); }
 
-// Leave-one-out "box" reduction over the D messages of a check row with a binary tree: `build` reduces subtrees
-// bottom-up, `down` hands every leaf the reduction of everything outside it.  The operator is the reference's
-// min' (Min.hs:89: sign product times minimum magnitude), exact in floating point and associative, so the result
-// equals foldr1 min' over the other entries bit for bit.  ~2.6 ops per edge at depth log2(D).
-template <typename T> struct OpBox { static __device__ __forceinline__ T f(T a, T b) { return FB<T>::box(a, b); } };
-template <typename T> struct OpAdd { static __device__ __forceinline__ T f(T a, T b) { return FB<T>::add(a, b); } };
-
-template <typename T, int LO, int HI, class Op = OpBox<T>> struct BoxTree {
-    static constexpr int MID = (LO + HI) / 2;
-    BoxTree<T, LO, MID, Op> l;
-    BoxTree<T, MID, HI, Op> r;
-    T m;
-    template <class A> __device__ __forceinline__ void build(const A &a)
-    {
-        l.build(a); r.build(a);
-        m = Op::f(l.m, r.m);
-    }
-    template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const
-    {
-        l.down(Op::f(o, r.m), emit);
-        r.down(Op::f(o, l.m), emit);
-    }
-    template <class Fn> __device__ __forceinline__ void down_root(Fn &&emit) const
-    {
-        l.down(r.m, emit);
-        r.down(l.m, emit);
-    }
-};
-template <typename T, int LO, class Op> struct BoxTree<T, LO, LO + 1, Op> {
-    T m;
-    template <class A> __device__ __forceinline__ void build(const A &a) { m = a(std::integral_constant<int, LO>{}); }
-    template <class Fn> __device__ __forceinline__ void down(T o, Fn &&emit) const { emit(std::integral_constant<int, LO>{}, o); }
-};
-
 // Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
 // round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
 // zero (punctured LLR, or a sum that cancels) is +0.0 in mu, and mu is never -0.0 (x + y = -0 needs both operands
 // -0, and negL = 0 - L is never -0).  Hence hard(lam) = (lam > 0) = sign bit of mu, and the syndrome parity of a
 // check row is the xor of the sign bits of its mu's: half a LOP3 per edge instead of a compare per edge.
-
-#include "spa_fp32.cuh"
-struct OpCompl { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-a, b, a + b); } };
-// the same on magnitudes (|.| is an operand modifier of FADD / FFMA): leaves may carry a payload in their sign bit
-struct OpComplAbs { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-fabsf(a), fabsf(b), fabsf(a) + fabsf(b)); } };
-// lg2((2 - c) / c) = 2 atanh(1 - c) / ln 2 (uncapped), and the reference's ceiling 2 * 18.714973875118524 in the same unit
-__device__ __forceinline__ float spa_mag_lg2(float c) { c = fabsf(c); return mufu_lg2(2.0f - c) - mufu_lg2(c); }
-#define SPA_CAP_LG2 54.0f   // 2 * 18.714973875118524 = ln((2 - 2^-53) / 2^-53) = 54 ln 2 to within 1e-16
 
 // Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
 // checks is unsatisfied by hard(lam).

@@ -16,12 +16,16 @@
 // variable update Orig.hs:95-98 (right fold: last row first, starting from the channel LLR).
 #include "common.cuh"
 #include <math.h>
+#include <utility>
 
 namespace ldpc {
 
-#include "spa_fp32.cuh"
+#include "bp_tree.cuh"
 
-static constexpr int TPB = 128;   // threads per block along the frame axis
+#ifndef STREAM_TPB
+#define STREAM_TPB 128
+#endif
+static constexpr int TPB = STREAM_TPB;   // threads per block along the frame axis
 
 template <typename T> struct Num;
 template <> struct Num<double> {
@@ -125,7 +129,8 @@ __device__ __forceinline__ T atanh_prime(T x)
     return y;
 }
 
-// Check-node update, one thread per (check, frame).
+// Check-node update, one thread per (check, frame): fall-back form with dynamic loops (rows wider than 32, and the
+// literal fp64 sum-product).  The staged kernels below are the ones that run for the codes of codes/.
 template <typename T, int ALGO, int MAXD>
 __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ ne,
                      const uint8_t *__restrict__ state, uint8_t *__restrict__ unsat, int F, int Bp, int skip_done)
@@ -207,6 +212,184 @@ __global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict
     lam[(size_t)j * Bp + f] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-staged kernels.  One CTA = TPB frames x CPC checks (VPC variables).  Every row a check touches is a contiguous
+// TPB*sizeof(T)-byte segment of the frame-minor arrays, so the whole working set of the CTA is fetched with 1-D bulk
+// copies (cp.async.bulk -> UBLKCP) signalled on one mbarrier, computed on from shared memory, and written back with
+// bulk stores.  Why: with per-thread loads the compiler interleaves uses with later loads (predicate and register
+// pressure heuristics), the in-order issue then stalls on a DRAM round trip several times per row and the kernel ran
+// at 2.7 TB/s with 56 % long-scoreboard stalls; with bulk copies all bytes of the CTA are in flight at once and no
+// register holds an address or a pending value.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Check-node update: CTA = CPC consecutive checks x TPB frames; thread = one frame, loops over the CPC checks.
+template <typename T, int ALGO, int MAXD, int CPC>
+__global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ ne,
+                                                const uint8_t *__restrict__ state, uint8_t *__restrict__ unsat,
+                                                int F, int Bp, int skip_done)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int S = MAXD + 2;
+    constexpr uint32_t ROW = TPB * sizeof(T);
+    T(*lam_s)[TPB] = reinterpret_cast<T(*)[TPB]>(smem_raw);                 // [CPC*MAXD][TPB]
+    T(*ne_s)[TPB] = lam_s + CPC * MAXD;                                     // [CPC*MAXD][TPB]
+    __shared__ int32_t s_rec[CPC * S];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, f0 = blockIdx.y * TPB, f = f0 + tid, m0 = blockIdx.x * CPC;
+    const int nchk = min(CPC, g.M - m0);
+    if (tid < nchk * S) s_rec[tid] = g.row_ell[(size_t)m0 * S + tid];       // one cooperative load: {b, d, columns} per check
+    if (tid == 0) mbar_init(&bar, 1);
+    const bool idle = f >= F || (skip_done && state[f]);
+    if (!__syncthreads_or(!idle)) return;                                   // every frame of the block has stopped
+    // producers: thread 0 fetches the posterior rows, thread 32 the message rows.  (Spreading the issue over all four
+    // warps was measured 25 % SLOWER: the copies of one thread pipeline well, and the other warps are better left idle.)
+    if (tid == 0) {
+        uint32_t rows = 0;
+        for (int c = 0; c < nchk; c++) rows += (uint32_t)s_rec[c * S + 1];
+        mbar_expect_tx(&bar, 2u * rows * ROW);
+        for (int c = 0; c < nchk; c++)
+            for (int k = 0; k < s_rec[c * S + 1]; k++)
+                bulk_g2s(lam_s[c * MAXD + k], lam + (size_t)s_rec[c * S + 2 + k] * Bp + f0, ROW, &bar);
+    } else if (tid == 32) {
+        for (int c = 0; c < nchk; c++)
+            for (int k = 0; k < s_rec[c * S + 1]; k++)
+                bulk_g2s(ne_s[c * MAXD + k], ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ROW, &bar);
+    }
+    mbar_wait(&bar, 0);
+    int par_any = 0;
+    for (int c = 0; c < nchk; c++) {
+        const int d = s_rec[c * S + 1];
+        // The row is padded to MAXD with the neutral element of the check operator, so the update is the same
+        // predicate-free leave-one-out tree as in the RESIDENT engine (~2.6 operations per edge).
+        T x[MAXD];
+        int par = 0;
+#pragma unroll
+        for (int k = 0; k < MAXD; k++) {
+            const T l = lam_s[c * MAXD + k][tid], n = ne_s[c * MAXD + k][tid];   // rows >= d: stale shared memory, masked below
+            par ^= (k < d) & (l > (T)0);                                        // syndrome of the CURRENT posteriors (Orig.hs:73-78)
+            x[k] = (k < d) ? -Num<T>::sub(l, n) : Num<T>::inf();                // x_j = -(lam_j - ne[m,j])   (Min.hs:80 / Orig.hs:84)
+        }
+        par_any |= par;
+        if constexpr (ALGO == LDPC_B200_ALGO_SPA) {
+            // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) (pad: x = +inf -> c = 0, the
+            // identity) combined leave-one-out in the tree; the sign of x_j rides in the sign bit of its complement;
+            // magnitude lg2((2-c)/c) capped at the reference's clamp and signed by one FMNMX.XORSIGN; times ln 2.
+            uint32_t sgn = 0;
+#pragma unroll
+            for (int k = 0; k < MAXD; k++) sgn ^= __float_as_uint((float)x[k]);
+            const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
+            float leaf[MAXD];
+#pragma unroll
+            for (int k = 0; k < MAXD; k++)
+                leaf[k] = __uint_as_float(__float_as_uint(spa_compl((float)x[k])) | (__float_as_uint((float)x[k]) & 0x80000000u));
+            BoxTree<float, 0, MAXD, OpComplAbs> tree;
+            tree.build([&](auto ki) { return leaf[decltype(ki)::value]; });
+            tree.down_root([&](auto ki, float others) {
+                constexpr int k = decltype(ki)::value;
+                const float w = FB<float>::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(leaf[k]) & 0x80000000u)));
+                if (k < d) ne_s[c * MAXD + k][tid] = (T)(w * 0.69314718055994531f);
+            });
+        } else {
+            // Min.hs:79-89: ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]; min' is exact and associative, pad = +inf
+            BoxTree<T, 0, MAXD> tree;
+            tree.build([&](auto ki) { return x[decltype(ki)::value]; });
+            tree.down_root([&](auto ki, T others) {
+                constexpr int k = decltype(ki)::value;
+                if (k < d) ne_s[c * MAXD + k][tid] = Num<T>::mul((T)-0.75, others);
+            });
+        }
+    }
+    if (par_any && !idle) unsat[f] = 1;                                     // k_status reads it after this kernel
+    // Frames of this block that have already stopped get their (never used again) messages overwritten too.
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < nchk; c++)
+            for (int k = 0; k < s_rec[c * S + 1]; k++)
+                bulk_s2g(ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ne_s[c * MAXD + k], ROW);
+        bulk_commit_wait_read();
+    }
+}
+
+// Variable-node update (Orig.hs:95-98): CTA = VPC consecutive variables x TPB frames.  Rows per variable: its channel
+// LLR and its (<= COL_ELL_D) messages in the order of the reference's right fold; the new posterior row goes back with a
+// bulk store.
+template <typename T, int VPC>
+__global__ void __launch_bounds__(TPB) k_vn_tma(DeviceGraph g, const T *__restrict__ L, const T *__restrict__ ne,
+                                                T *__restrict__ lam, const uint8_t *__restrict__ state,
+                                                int F, int Bp, int skip_done)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = DeviceGraph::COL_ELL_D, S = D + 1, R = D + 1;        // R rows per variable: [0] = L, [1..] = messages
+    constexpr uint32_t ROW = TPB * sizeof(T);
+    T(*rows)[TPB] = reinterpret_cast<T(*)[TPB]>(smem_raw);                  // [VPC*R][TPB]
+    __shared__ int32_t s_rec[VPC * S];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, f0 = blockIdx.y * TPB, f = f0 + tid, j0 = blockIdx.x * VPC;
+    const int nvar = min(VPC, g.N - j0);
+    if (tid < nvar * S) s_rec[tid] = g.col_ell[(size_t)j0 * S + tid];
+    if (tid == 0) mbar_init(&bar, 1);
+    const bool idle = f >= F || (skip_done && state[f]);
+    if (!__syncthreads_or(!idle)) return;
+    if (tid == 0) {
+        uint32_t n = 0;
+        for (int v = 0; v < nvar; v++) n += 1u + (uint32_t)s_rec[v * S];
+        mbar_expect_tx(&bar, n * ROW);
+        for (int v = 0; v < nvar; v++) bulk_g2s(rows[v * R], L + (size_t)(j0 + v) * Bp + f0, ROW, &bar);
+    } else if (tid == 32) {
+        for (int v = 0; v < nvar; v++)
+            for (int i = 0; i < s_rec[v * S]; i++)
+                bulk_g2s(rows[v * R + 1 + i], ne + (size_t)s_rec[v * S + 1 + i] * Bp + f0, ROW, &bar);
+    }
+    mbar_wait(&bar, 0);
+    for (int v = 0; v < nvar; v++) {
+        const int d = s_rec[v * S];
+        T acc = rows[v * R][tid];
+#pragma unroll
+        for (int i = 0; i < D; i++) if (i < d) acc = Num<T>::add(rows[v * R + 1 + i][tid], acc);   // last check first
+        rows[v * R][tid] = acc;
+    }
+    // (frames of this block that have already stopped get a posterior they never read again)
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int v = 0; v < nvar; v++) bulk_s2g(lam + (size_t)(j0 + v) * Bp + f0, rows[v * R], ROW);
+        bulk_commit_wait_read();
+    }
+}
+
 __global__ void k_finish(const uint8_t *__restrict__ state, const int32_t *__restrict__ iters,
                          int32_t *__restrict__ out_iters, uint8_t *__restrict__ out_conv, int F)
 {
@@ -222,6 +405,12 @@ int stream_alloc(ldpc_b200_decoder *d)
     if (s.L) return 0;
     const ldpc_b200_code *c = d->code;
     int Bp = ((d->max_batch + TPB - 1) / TPB) * TPB;
+    // Row stride of the frame-minor arrays.  All CTAs in flight work on the same block of frames, i.e. on the same offset
+    // inside every row; with a power-of-two stride those addresses differ only in their high bits and pile onto a few
+    // DRAM channels.  An odd number of TPB-frame blocks per row spreads consecutive rows over all channels.
+#ifndef STREAM_NO_SKEW
+    if (((Bp / TPB) & 1) == 0) Bp += TPB;
+#endif
     size_t es = elem_size(d->precision);
     s.Bp = Bp;
     LDPC_CUDA(cudaMalloc(&s.L, (size_t)c->N * Bp * es));
@@ -242,17 +431,59 @@ void stream_free(ldpc_b200_decoder *d)
     s = StreamBuffers();
 }
 
-template <typename T, int ALGO>
-static int launch_cn(ldpc_b200_decoder *d, dim3 grid, int F, int skip_done)
+template <typename T, int ALGO, int MAXD, int CPC>
+static int launch_cn_tma(ldpc_b200_decoder *d, int fb, int F, int skip_done)
 {
     const DeviceGraph &g = d->code->g;
     StreamBuffers &s = d->sb;
+    auto kern = k_cn_tma<T, ALGO, MAXD, CPC>;
+    const size_t smem = (size_t)2 * CPC * MAXD * TPB * sizeof(T);
+    if (smem > 48 * 1024) LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+    kern<<<dim3((g.M + CPC - 1) / CPC, fb), TPB, smem, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
+    d->launches++;
+    return 0;
+}
+
+template <typename T, int ALGO>
+static int launch_cn(ldpc_b200_decoder *d, int fb, int F, int skip_done)
+{
+    const DeviceGraph &g = d->code->g;
+    StreamBuffers &s = d->sb;
+    constexpr bool LITERAL64 = (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 8);   // fp64 sum-product keeps the literal O(d^2) form
+    if constexpr (!LITERAL64) {
+        switch (g.row_ell_d) {     // fixed-stride record class chosen at code creation (0: rows wider than 32)
+        case 4: return launch_cn_tma<T, ALGO, 4, 8>(d, fb, F, skip_done);
+        case 8: return launch_cn_tma<T, ALGO, 8, 4>(d, fb, F, skip_done);
+        case 18: return launch_cn_tma<T, ALGO, 18, 1>(d, fb, F, skip_done);
+        case 32: return launch_cn_tma<T, ALGO, 32, 1>(d, fb, F, skip_done);
+        default: break;
+        }
+    }
+    dim3 grid(g.M, fb);
     if (g.max_row_deg <= 8)
         k_cn<T, ALGO, 8><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
     else if (g.max_row_deg <= 32)
         k_cn<T, ALGO, 32><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
     else
         k_cn<T, ALGO, 128><<<grid, TPB, 0, d->stream>>>(g, (const T *)s.lam, (T *)s.ne, s.state, s.unsat, F, s.Bp, skip_done);
+    d->launches++;
+    return 0;
+}
+
+template <typename T>
+static int launch_vn(ldpc_b200_decoder *d, int fb, int F, int skip_done)
+{
+    const DeviceGraph &g = d->code->g;
+    StreamBuffers &s = d->sb;
+    if (g.max_col_deg <= DeviceGraph::COL_ELL_D) {
+        constexpr int VPC = 4;
+        auto kern = k_vn_tma<T, VPC>;
+        const size_t smem = (size_t)VPC * (DeviceGraph::COL_ELL_D + 1) * TPB * sizeof(T);
+        if (smem > 48 * 1024) LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3((g.N + VPC - 1) / VPC, fb), TPB, smem, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
+    } else {
+        k_vn<T><<<dim3(g.N, fb), TPB, 0, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
+    }
     d->launches++;
     return 0;
 }
@@ -293,8 +524,9 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             if (M > 0) { k_syndrome<T><<<gcn, TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
         } else if (M > 0) {
             // converged frames are skipped via `state` when early exit is on; with early_exit = 0 they keep iterating
-            if (d->algo == LDPC_B200_ALGO_SPA) launch_cn<T, LDPC_B200_ALGO_SPA>(d, gcn, F, skip);
-            else launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, gcn, F, skip);
+            int rc = d->algo == LDPC_B200_ALGO_SPA ? launch_cn<T, LDPC_B200_ALGO_SPA>(d, fb, F, skip)
+                                                   : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
+            if (rc) return rc;
         }
         LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));
         k_status<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.unsat, s.iters, s.active, n, max_iters, F);
@@ -307,8 +539,7 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             LDPC_CUDA(cudaStreamSynchronize(st));
             if (active == 0) break;
         }
-        k_vn<T><<<dim3(N, fb), TPB, 0, st>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, Bp, skip);
-        d->launches++;
+        { int rc = launch_vn<T>(d, fb, F, skip); if (rc) return rc; }
         if (h_c2v || h_lam) {   // trace of frame 0: column 0 of the frame-minor arrays
             size_t need = (size_t)(E > N ? E : N);
             tmp.resize(need);
