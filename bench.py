@@ -271,17 +271,23 @@ def main():
     except Exception:
         pass
 
-    # ---------------- e2e: host float64 LLRs -> ldpc_b200_decode -> host decisions ----------------
+    # ---------------- e2e: the reference-facing plugin call, host buffers in and out ----------------
+    # ECC record `decode` (Utils.hs:62-72) of "ldpc/b200-minsum/jpl.4096.4.5/20/4/5": c_length = 5120 received float64
+    # LLRs per frame in (pinned host memory), the first message_length = 4096 decided bits per frame out.
+    from ecc_ldpc_b200 import ecc as ecc_mod
     Be = args.e2e_frames
-    h_llr = torch.empty((Be, code.N), dtype=torch.float64).pin_memory()
-    h_llr.copy_(d_llr[:Be].double().cpu())
-    h_bits = torch.empty((Be, code.N), dtype=torch.uint8).pin_memory()
+    rec = ecc_mod.match("ldpc/b200-minsum/%s/%d/4/5" % (CODE, MAX_ITERS), max_batch=min(Be, 4096))[0]
+    assert rec.codeword_length == N_TX and rec.message_length == code.K, (rec.codeword_length, rec.message_length)
+    h_rx = torch.empty((Be, N_TX), dtype=torch.float64).pin_memory()
+    h_rx.copy_(d_llr[:Be, :N_TX].double().cpu())
+    h_msg = torch.empty((Be, code.K), dtype=torch.uint8).pin_memory()
+    h_flags = torch.empty(Be, dtype=torch.uint8).pin_memory()
     h_iters = torch.empty(Be, dtype=torch.int32).pin_memory()
     h_conv = torch.empty(Be, dtype=torch.uint8).pin_memory()
     L = lib.load()
 
     def step_e2e():
-        lib.check(L.ldpc_b200_decode(dec.h, MAX_ITERS, Be, h_llr.data_ptr(), h_bits.data_ptr(), h_iters.data_ptr(), h_conv.data_ptr()))
+        lib.check(L.ldpc_b200_ecc_decode(rec.h, Be, h_rx.data_ptr(), N_TX, h_msg.data_ptr(), h_flags.data_ptr()))
 
     for _ in range(max(1, args.warmup)):
         step_e2e()
@@ -295,9 +301,14 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_fps = Be * world * e2e_steps / float(dt.item())
-    e2e = {"value": e2e_fps * code.K / 1e9, "unit": UNIT, "h2d_bytes_per_step": Be * code.N * 8,
-           "d2h_bytes_per_step": Be * (code.N + 5), "frames_per_step": Be,
-           "api": "ldpc_b200_decode (float64 LLRs, pinned host buffers; uint8 decisions + iters + flags back)"}
+    # the message bits of the e2e call must be the ones the device-resident path decided for the same frames
+    dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=True, d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
+    dec.sync()
+    ref_bits = lib.unpack_bits(d_bits[:256].cpu().numpy().view(np.uint32), code.N)[:, :code.K]
+    e2e_same = bool((h_msg[:256].numpy() == ref_bits).all())
+    e2e = {"value": e2e_fps * code.K / 1e9, "unit": UNIT, "h2d_bytes_per_step": Be * N_TX * 8,
+           "d2h_bytes_per_step": Be * code.K, "frames_per_step": Be, "matches_device_path": e2e_same,
+           "api": "ldpc_b200_ecc_decode = ECC.decode of ldpc/b200-minsum/%s/%d/4/5 (float64 received LLRs in pinned host memory; message bits back)" % (CODE, MAX_ITERS)}
 
     # ---------------- extra operating points with early exit (reference semantics) ----------------
     extra = {}

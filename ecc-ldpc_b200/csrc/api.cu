@@ -404,8 +404,12 @@ static int ensure_pipe(ldpc_b200_decoder *d, bool want_bytes)
 // Shared body of the two host-buffer entry points: frames go through in chunks on three streams so that the
 // H2D copy of chunk k+1, the decode of chunk k and the D2H copy of chunk k-1 overlap (pinned host buffers make
 // the copies truly asynchronous; pageable ones still work).
+// in_stride / in_take (elements): host row stride and number of leading LLRs per frame that exist on the host; the
+// remaining N - in_take positions are punctured (LLR 0, Utils.hs:55) and never cross PCIe.  out_take: decision bytes
+// per frame copied back (the first m_length, Utils.hs:72), host row stride = out_take.  0 = whole rows (N).
 static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const void *llr, bool is_double,
-                       uint8_t *bits_bytes, uint32_t *bits_packed, int32_t *iters, uint8_t *converged)
+                       uint8_t *bits_bytes, uint32_t *bits_packed, int32_t *iters, uint8_t *converged,
+                       int in_stride = 0, int in_take = 0, int out_take = 0)
 {
     if (!d || max_iters < 0 || n_frames < 0 || (n_frames && (!llr || (!bits_bytes && !bits_packed)))) { set_error("decode: bad arguments"); return LDPC_B200_EINVAL; }
     if (n_frames == 0) return 0;
@@ -434,7 +438,14 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         ldpc_b200_decoder::PipeSet &s = d->pipe[k & 1];
         rc = harvest(s);                         // also guarantees the set's buffers are free again
         if (rc) break;
-        LDPC_CUDA(cudaMemcpyAsync(s.d_in, (const char *)llr + (size_t)f0 * N * in_es, (size_t)F * N * in_es, cudaMemcpyHostToDevice, d->copy_stream));
+        if (in_take > 0 && (in_take < N || in_stride != N)) {
+            if (in_take < N)
+                LDPC_CUDA(cudaMemset2DAsync((char *)s.d_in + (size_t)in_take * in_es, (size_t)N * in_es, 0, (size_t)(N - in_take) * in_es, F, d->copy_stream));
+            LDPC_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)N * in_es, (const char *)llr + (size_t)f0 * in_stride * in_es, (size_t)in_stride * in_es,
+                                        (size_t)in_take * in_es, F, cudaMemcpyHostToDevice, d->copy_stream));
+        } else {
+            LDPC_CUDA(cudaMemcpyAsync(s.d_in, (const char *)llr + (size_t)f0 * N * in_es, (size_t)F * N * in_es, cudaMemcpyHostToDevice, d->copy_stream));
+        }
         LDPC_CUDA(cudaEventRecord(s.h2d_done, d->copy_stream));
         LDPC_CUDA(cudaStreamWaitEvent(d->stream, s.h2d_done, 0));
         d->launches = 0;
@@ -445,7 +456,9 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         LDPC_CUDA(cudaEventRecord(s.t1, d->stream));
         total_launches += d->launches;
         LDPC_CUDA(cudaStreamWaitEvent(d->d2h_stream, s.t1, 0));
-        if (bits_bytes) LDPC_CUDA(cudaMemcpyAsync(bits_bytes + (size_t)f0 * N, s.d_bytes, (size_t)F * N, cudaMemcpyDeviceToHost, d->d2h_stream));
+        if (bits_bytes && out_take > 0 && out_take < N)
+            LDPC_CUDA(cudaMemcpy2DAsync(bits_bytes + (size_t)f0 * out_take, out_take, s.d_bytes, N, out_take, F, cudaMemcpyDeviceToHost, d->d2h_stream));
+        else if (bits_bytes) LDPC_CUDA(cudaMemcpyAsync(bits_bytes + (size_t)f0 * N, s.d_bytes, (size_t)F * N, cudaMemcpyDeviceToHost, d->d2h_stream));
         if (bits_packed) LDPC_CUDA(cudaMemcpyAsync(bits_packed + (size_t)f0 * W, s.d_bits, (size_t)F * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->d2h_stream));
         if (iters) LDPC_CUDA(cudaMemcpyAsync(iters + f0, s.d_iters, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, d->d2h_stream));
         if (converged) LDPC_CUDA(cudaMemcpyAsync(converged + f0, s.d_conv, (size_t)F, cudaMemcpyDeviceToHost, d->d2h_stream));
@@ -467,6 +480,14 @@ int ldpc_b200_decode(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const 
                      int32_t *iters, uint8_t *converged)
 {
     return decode_host(d, max_iters, n_frames, llr, true, bits, nullptr, iters, converged);
+}
+
+/* internal (host_ecc.cu): the mkLDPC decode closure in one pass -- only the transmitted LLRs go up, only the message
+ * bits come back (Utils.hs:55,68-72). */
+int ldpc_b200_decode_punctured(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const double *rx, int rx_stride, int take,
+                               uint8_t *msg_bits, int k_take)
+{
+    return decode_host(d, max_iters, n_frames, rx, true, msg_bits, nullptr, nullptr, nullptr, rx_stride, take, k_take);
 }
 
 int ldpc_b200_decode_f32(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const float *llr, uint32_t *bits_packed,

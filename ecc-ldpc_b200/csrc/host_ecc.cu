@@ -380,6 +380,9 @@ static int ensure_device(ldpc_b200_ecc *e)
     return ldpc_b200_decoder_create(e->dcode, e->algo, e->precision, e->max_batch, &e->dec);
 }
 
+extern "C" int ldpc_b200_decode_punctured(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const double *rx, int rx_stride, int take,
+                                          uint8_t *msg_bits, int k_take);
+
 extern "C" int ldpc_b200_ecc_decode(ldpc_b200_ecc_t *e, int n_frames, const double *rx, int rx_len, uint8_t *out, uint8_t *flags)
 {
     if (!e || n_frames < 0 || (n_frames && (!rx || !out)) || rx_len < 0) { set_error("ecc_decode: bad arguments"); return LDPC_B200_EINVAL; }
@@ -388,16 +391,12 @@ extern "C" int ldpc_b200_ecc_decode(ldpc_b200_ecc_t *e, int n_frames, const doub
     if (rc) return rc;
     int N = e->N, K = e->K;
     int take = std::min(std::min(e->c_length, rx_len), N);
-    // unpuncture xs = take c_length xs ++ replicate (N - c_length) 0   (Utils.hs:55)
-    std::vector<double> full((size_t)n_frames * N, 0.0);
-    for (int f = 0; f < n_frames; f++) memcpy(&full[(size_t)f * N], rx + (size_t)f * rx_len, sizeof(double) * take);
-    std::vector<uint8_t> bits((size_t)n_frames * N);
-    rc = ldpc_b200_decode(e->dec, e->max_iters, n_frames, full.data(), bits.data(), nullptr, nullptr);
+    // unpuncture xs = take c_length xs ++ replicate (N - c_length) 0   (Utils.hs:55); take m_length (Utils.hs:72):
+    // the padding zeros are written on the device and only the message bits are copied back
+    if (take <= 0) { set_error("ecc_decode: no received values"); return LDPC_B200_EINVAL; }
+    rc = ldpc_b200_decode_punctured(e->dec, e->max_iters, n_frames, rx, rx_len, take, out, K);
     if (rc) return rc;
-    for (int f = 0; f < n_frames; f++) {
-        memcpy(out + (size_t)f * K, &bits[(size_t)f * N], K);        // take m_length (Utils.hs:72)
-        if (flags) flags[f] = 1;                                       // every decoder returns Just
-    }
+    if (flags) memset(flags, 1, (size_t)n_frames);                     // every decoder returns Just
     return 0;
 }
 

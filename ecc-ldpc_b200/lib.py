@@ -24,7 +24,7 @@ EXPORTS = [
     "ldpc_b200_device_count", "ldpc_b200_code_create_csr", "ldpc_b200_code_create_qc",
     "ldpc_b200_code_destroy", "ldpc_b200_code_info", "ldpc_b200_decoder_create",
     "ldpc_b200_decoder_set_engine", "ldpc_b200_decoder_engine", "ldpc_b200_decoder_destroy",
-    "ldpc_b200_decode", "ldpc_b200_decode_f32", "ldpc_b200_decode_trace", "ldpc_b200_decode_device",
+    "ldpc_b200_decode", "ldpc_b200_decode_punctured", "ldpc_b200_decode_f32", "ldpc_b200_decode_trace", "ldpc_b200_decode_device",
     "ldpc_b200_decoder_sync", "ldpc_b200_decoder_last_timing", "ldpc_b200_generate_llr",
     "ldpc_b200_simulate", "ldpc_b200_simulate_device", "ldpc_b200_simulate_multi", "ldpc_b200_simulate_multi_release",
     "ldpc_b200_count_errors", "ldpc_b200_malloc", "ldpc_b200_free",
@@ -83,6 +83,7 @@ def load():
     L.ldpc_b200_decoder_destroy.restype = None
     L.ldpc_b200_decode.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.ldpc_b200_decode_f32.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.ldpc_b200_decode_punctured.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32]
     L.ldpc_b200_decode_trace.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.ldpc_b200_decode_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.ldpc_b200_decoder_sync.argtypes = [vp]

@@ -100,6 +100,11 @@ int ldpc_b200_decode(ldpc_b200_decoder_t *dec, int max_iters, int n_frames, cons
 /* Same with float32 LLRs in and bit-packed decisions out (bit j of frame f = word f*ceil(N/32)+j/32, bit j%32). */
 int ldpc_b200_decode_f32(ldpc_b200_decoder_t *dec, int max_iters, int n_frames, const float *llr,
                          uint32_t *bits_packed, int32_t *iters, uint8_t *converged);
+/* The decode closure of mkLDPC in one pass (src/ECC/Code/LDPC/Utils.hs:55,68-72): rx holds, per frame, `take`
+ * received LLRs at a row stride of rx_stride doubles; the N - take punctured positions get LLR 0 on the device and never
+ * cross PCIe; msg_bits receives the first k_take decisions of every frame (n_frames x k_take bytes). */
+int ldpc_b200_decode_punctured(ldpc_b200_decoder_t *dec, int max_iters, int n_frames, const double *rx, int rx_stride,
+                               int take, uint8_t *msg_bits, int k_take);
 
 /* One frame, with the messages of every executed iteration t (0-based): c2v[t*E + e] = ne'[edge e] in
  * reference edge order (row-major, ascending column), lam[t*N + j] = lam'[j]. Arrays hold max_iters rows.
