@@ -287,7 +287,11 @@ int ldpc_b200_code_info(const ldpc_b200_code_t *c, int *M, int *N, int *E, int *
 int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precision, int max_batch, ldpc_b200_decoder_t **out)
 {
     if (!code || !out || max_batch <= 0) { set_error("decoder_create: bad arguments"); return LDPC_B200_EINVAL; }
-    if (algo != LDPC_B200_ALGO_SPA && algo != LDPC_B200_ALGO_MINSUM) { set_error("decoder_create: unknown algo %d", algo); return LDPC_B200_EINVAL; }
+    if (algo != LDPC_B200_ALGO_SPA && algo != LDPC_B200_ALGO_MINSUM && algo != LDPC_B200_ALGO_SPA_CM) { set_error("decoder_create: unknown algo %d", algo); return LDPC_B200_EINVAL; }
+    if (algo == LDPC_B200_ALGO_SPA_CM && precision != LDPC_B200_PREC_FP64) {
+        set_error("decoder_create: the cached-product sum-product (CachedMult.hs) is a float64 verification variant; use LDPC_B200_ALGO_SPA for float32");
+        return LDPC_B200_EUNSUPPORTED;
+    }
     if (precision != LDPC_B200_PREC_FP64 && precision != LDPC_B200_PREC_FP32) { set_error("decoder_create: unknown precision %d", precision); return LDPC_B200_EINVAL; }
     int rc = require_init();
     if (rc) return rc;

@@ -690,7 +690,7 @@ int resident_kind_for(const ldpc_b200_code *c)
 bool resident_supports(const ldpc_b200_decoder *d)
 {
     // min-sum: fp32 and fp64; sum-product: fp32 only (fp64 sum-product is the STREAM engine's literal form)
-    return d->code->resident_kind != 0 &&
+    return d->code->resident_kind != 0 && d->algo != LDPC_B200_ALGO_SPA_CM &&
            (d->algo == LDPC_B200_ALGO_MINSUM || d->precision == LDPC_B200_PREC_FP32);
 }
 

@@ -168,6 +168,29 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
             ne[(size_t)(b + k) * Bp + f] = (T)v;
             suf = fmaf(-suf, c[k], suf + c[k]);
         }
+    } else if (ALGO == LDPC_B200_ALGO_SPA_CM) {
+        // Fast/CachedMult.hs:248-261: the row's StableDiv product (worst term held out, CachedMult.hs:25-56), folded from
+        // the right in ascending column order, divided by the edge's own tanh.
+        if (d <= 0) return;
+        T t[MAXD];
+        for (int k = 0; k < d; k++) {
+            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            t[k] = Num<T>::tanh_(-(v / (T)2));
+        }
+        T wa, wb;                                                       // lit x | x >= 1 = (1, x) | otherwise = (x, 1)
+        if (t[d - 1] >= (T)1) { wa = (T)1; wb = t[d - 1]; } else { wa = t[d - 1]; wb = (T)1; }
+        for (int k = d - 2; k >= 0; k--) {                              // smult (lit t[k]) acc
+            T la, lb;
+            if (t[k] >= (T)1) { la = (T)1; lb = t[k]; } else { la = t[k]; lb = (T)1; }
+            T mn, mx;
+            if (Num<T>::abs_(la) < Num<T>::abs_(wa)) { mn = la; mx = wa; } else { mn = wa; mx = la; }
+            wb = Num<T>::mul(Num<T>::mul(lb, mx), wb);
+            wa = mn;
+        }
+        for (int k = 0; k < d; k++) {                                   // sdiv (a,b) c | a == c = b | otherwise = a * (b / c)
+            T q = (wa == t[k]) ? wb : Num<T>::mul(wa, wb / t[k]);
+            ne[(size_t)(b + k) * Bp + f] = (T)-2 * atanh_prime<T>(q);
+        }
     } else if (ALGO == LDPC_B200_ALGO_SPA) {
         // Orig.hs:86-91: tanh(-((lam_j - ne[m,j]) / 2)) per edge, leave-one-out LEFT fold of (*) from 1.
         T t[MAXD];
@@ -200,16 +223,26 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
 }
 
 // Orig.hs:95-98: lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))). One thread per (variable, frame).
-template <typename T>
+// ARRAYLET: the association of the arraylet decoders instead, L_j + (ne'[m1] + (ne'[m2] + ... + ne'[mk]))
+// (Fast/CachedMult.hs:263-264 = Fast/Arraylet.hs:185-186).
+template <typename T, bool ARRAYLET>
 __global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict__ ne, T *__restrict__ lam,
                      const uint8_t *__restrict__ state, int F, int Bp, int skip_done)
 {
     int f = blockIdx.y * TPB + threadIdx.x, j = blockIdx.x;
     if (f >= F) return;
     if (skip_done && state[f]) return;
-    T acc = L[(size_t)j * Bp + f];
-    for (int q = g.col_ptr[j + 1] - 1; q >= g.col_ptr[j]; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
-    lam[(size_t)j * Bp + f] = acc;
+    const int q0 = g.col_ptr[j], q1 = g.col_ptr[j + 1];
+    if (ARRAYLET) {
+        if (q1 == q0) { lam[(size_t)j * Bp + f] = L[(size_t)j * Bp + f]; return; }
+        T acc = ne[(size_t)g.col_edge[q1 - 1] * Bp + f];
+        for (int q = q1 - 2; q >= q0; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
+        lam[(size_t)j * Bp + f] = Num<T>::add(L[(size_t)j * Bp + f], acc);
+    } else {
+        T acc = L[(size_t)j * Bp + f];
+        for (int q = q1 - 1; q >= q0; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
+        lam[(size_t)j * Bp + f] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -449,7 +482,8 @@ static int launch_cn(ldpc_b200_decoder *d, int fb, int F, int skip_done)
 {
     const DeviceGraph &g = d->code->g;
     StreamBuffers &s = d->sb;
-    constexpr bool LITERAL64 = (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 8);   // fp64 sum-product keeps the literal O(d^2) form
+    // fp64 sum-product keeps the literal O(d^2) form; the cached-product variant is a verification statement too
+    constexpr bool LITERAL64 = (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 8) || ALGO == LDPC_B200_ALGO_SPA_CM;
     if constexpr (!LITERAL64) {
         switch (g.row_ell_d) {     // fixed-stride record class chosen at code creation (0: rows wider than 32)
         case 4: return launch_cn_tma<T, ALGO, 4, 8>(d, fb, F, skip_done);
@@ -475,14 +509,16 @@ static int launch_vn(ldpc_b200_decoder *d, int fb, int F, int skip_done)
 {
     const DeviceGraph &g = d->code->g;
     StreamBuffers &s = d->sb;
-    if (g.max_col_deg <= DeviceGraph::COL_ELL_D) {
+    if (d->algo == LDPC_B200_ALGO_SPA_CM) {
+        k_vn<T, true><<<dim3(g.N, fb), TPB, 0, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
+    } else if (g.max_col_deg <= DeviceGraph::COL_ELL_D) {
         constexpr int VPC = 4;
         auto kern = k_vn_tma<T, VPC>;
         const size_t smem = (size_t)VPC * (DeviceGraph::COL_ELL_D + 1) * TPB * sizeof(T);
         if (smem > 48 * 1024) LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dim3((g.N + VPC - 1) / VPC, fb), TPB, smem, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
     } else {
-        k_vn<T><<<dim3(g.N, fb), TPB, 0, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
+        k_vn<T, false><<<dim3(g.N, fb), TPB, 0, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
     }
     d->launches++;
     return 0;
@@ -524,8 +560,9 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             if (M > 0) { k_syndrome<T><<<gcn, TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
         } else if (M > 0) {
             // converged frames are skipped via `state` when early exit is on; with early_exit = 0 they keep iterating
-            int rc = d->algo == LDPC_B200_ALGO_SPA ? launch_cn<T, LDPC_B200_ALGO_SPA>(d, fb, F, skip)
-                                                   : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
+            int rc = d->algo == LDPC_B200_ALGO_SPA      ? launch_cn<T, LDPC_B200_ALGO_SPA>(d, fb, F, skip)
+                     : d->algo == LDPC_B200_ALGO_SPA_CM ? launch_cn<T, LDPC_B200_ALGO_SPA_CM>(d, fb, F, skip)
+                                                        : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
             if (rc) return rc;
         }
         LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));

@@ -50,7 +50,12 @@ enum {
     LDPC_B200_EUNSUPPORTED = -5
 };
 
-enum { LDPC_B200_ALGO_SPA = 0, LDPC_B200_ALGO_MINSUM = 1 };
+enum {
+    LDPC_B200_ALGO_SPA = 0,     /* sum-product, src/ECC/Code/LDPC/Reference/Orig.hs:81-92 */
+    LDPC_B200_ALGO_MINSUM = 1,  /* normalised min-sum alpha = 3/4, src/ECC/Code/LDPC/Reference/Min.hs:75-89 */
+    LDPC_B200_ALGO_SPA_CM = 2   /* sum-product with the cached StableDiv row product of `ldpc/arraylet-cm`
+                                   (src/ECC/Code/LDPC/Fast/CachedMult.hs:25-56,248-264); float64 only */
+};
 enum { LDPC_B200_PREC_FP64 = 0, LDPC_B200_PREC_FP32 = 1 };
 /* STREAM   : any H; messages live in HBM, frame-minor layout, one launch per phase.
  * RESIDENT : quasi-cyclic H with single-weight circulants; the whole frame state stays in

@@ -21,7 +21,8 @@
  *                             AWGN, decode, count errors over the first message_length bits
  *   ldpc_b200_ber_line        the result line of eccPrinter as visible in NOTES.txt:3
  *
- * Decoder names registered: b200-minsum, b200-spa (fp32), b200-minsum-fp64, b200-spa-fp64.
+ * Decoder names registered: b200-minsum, b200-spa (fp32), b200-minsum-fp64, b200-spa-fp64, b200-spa-cm-fp64
+ * (the cached-product variant of src/ECC/Code/LDPC/Fast/CachedMult.hs).
  */
 #ifndef LDPC_B200_ECC_H
 #define LDPC_B200_ECC_H

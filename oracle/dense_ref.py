@@ -37,9 +37,57 @@ def foldr1(f, xs):
     return acc
 
 
+# Fast/CachedMult.hs:25-56 -- StableDiv as a (worst, product-of-the-rest) pair
+def sd_lit(x):
+    return (1.0, x) if x >= 1 else (x, 1.0)
+
+
+def sd_mult(p, q):
+    (a, b), (c, d) = p, q
+    mn, mx = (a, c) if abs(a) < abs(c) else (c, a)          # absMinMax
+    return (mn, b * mx * d)
+
+
+def sd_div(p, c):
+    a, b = p
+    return b if a == c else a * (b / c)
+
+
+def ldpc_cached_mult(h_dense, max_iterations, orig_lam, trace=None):
+    """Fast/CachedMult.hs:233-264 (`ldpc/arraylet-cm`) on the expanded matrix: the check update divides the row's
+    StableDiv product by the edge's own tanh; the posterior is orig_lam + foldr1 (+) (column of ne')."""
+    M, N = len(h_dense), len(h_dense[0])
+    ones = [[n for n in range(N) if h_dense[m][n]] for m in range(M)]
+    cols = [[m for m in range(M) if h_dense[m][n]] for n in range(N)]
+    ne = {(m, n): 0.0 for m in range(M) for n in ones[m]}
+    lam = list(orig_lam)
+    n_it = 0
+    while True:
+        if all(sum(1 for j in ones[m] if hard(lam[j])) % 2 == 0 for m in range(M)):
+            return [1 if hard(v) else 0 for v in lam], n_it, True
+        if n_it >= max_iterations:
+            return [1 if hard(v) else 0 for v in orig_lam], n_it, False
+        t = {(m, n): math.tanh(-((lam[n] - ne[(m, n)]) / 2)) for (m, n) in ne}
+        ne2 = {}
+        for m in range(M):
+            if not ones[m]:
+                continue
+            row = foldr1(sd_mult, [sd_lit(t[(m, n)]) for n in ones[m]])
+            for n in ones[m]:
+                ne2[(m, n)] = -2 * atanh_prime(sd_div(row, t[(m, n)]))
+        lam2 = [orig_lam[j] + foldr1(lambda x, y: x + y, [ne2[(m, j)] for m in cols[j]]) if cols[j] else orig_lam[j]
+                for j in range(N)]
+        if trace is not None:
+            trace.append((dict(ne2), list(lam2)))
+        ne, lam = ne2, lam2
+        n_it += 1
+
+
 def ldpc(h_dense, algo, max_iterations, orig_lam, trace=None):
     """Returns (bits, iterations, converged). algo: 'spa' (Orig.hs) or 'min' (Min.hs).
     trace: optional list; gets (ne' as {(m,n): v}, lam' list) appended per iteration."""
+    if algo in ("spa_cm", "cm"):
+        return ldpc_cached_mult(h_dense, max_iterations, orig_lam, trace)
     M = len(h_dense)
     N = len(h_dense[0])
     ones = [[n for n in range(N) if h_dense[m][n]] for m in range(M)]      # a ! (m,j) == 1, ascending j

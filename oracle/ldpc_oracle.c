@@ -124,6 +124,53 @@ static void cn_update_literal(const oracle_code *c, int algo, const double *lam,
     }
 }
 
+/* Fast/CachedMult.hs:25-56: StableDiv = (the value closest to zero, the product of all the others).
+ *   lit x | x >= 1 = (1, x) | otherwise = (x, 1)
+ *   smult (a,b) (c,d) = (minOfMins, b * maxOfMins * d)  where (minOfMins, maxOfMins) = absMinMax a c
+ *   absMinMax x y | abs x < abs y = (x, y) | otherwise = (y, x)
+ *   sdiv (a,b) c | a == c = b | otherwise = a * (b / c)                                         */
+typedef struct { double a, b; } stable_div;
+static inline stable_div sd_lit(double x) { stable_div r; if (x >= 1) { r.a = 1; r.b = x; } else { r.a = x; r.b = 1; } return r; }
+static inline stable_div sd_mult(stable_div p, stable_div q)
+{
+    double mn, mx;
+    if (fabs(p.a) < fabs(q.a)) { mn = p.a; mx = q.a; } else { mn = q.a; mx = p.a; }
+    stable_div r; r.a = mn; r.b = (p.b * mx) * q.b;
+    return r;
+}
+static inline double sd_div(stable_div p, double c) { return p.a == c ? p.b : p.a * (p.b / c); }
+
+/* Fast/CachedMult.hs:248-261 (`ldpc/arraylet-cm`): sum-product whose leave-one-out product is
+ * (product of the whole row) / (own term), the row product kept as a StableDiv:
+ *   t[m,n]   = tanh (- ((lam_n - ne[m,n]) / 2))
+ *   row m    = foldr1 smult [ lit t[m,n] | n ascending ]            (foldColsMatrixletU, :193-197)
+ *   ne'[m,n] = -2 * atanh' (row m `sdiv` t[m,n])                                                  */
+static void cn_update_cached_mult(const oracle_code *c, const double *lam, const double *ne, double *ne2)
+{
+    double t[4096];
+    for (int m = 0; m < c->M; m++) {
+        int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
+        if (d <= 0) continue;
+        for (int k = 0; k < d; k++) t[k] = tanh(-((lam[c->col_idx[b + k]] - ne[b + k]) / 2));
+        stable_div acc = sd_lit(t[d - 1]);
+        for (int k = d - 2; k >= 0; k--) acc = sd_mult(sd_lit(t[k]), acc);
+        for (int k = 0; k < d; k++) ne2[b + k] = -2 * atanh_prime(sd_div(acc, t[k]));
+    }
+}
+
+/* Fast/CachedMult.hs:263-264 (same in Fast/Arraylet.hs:185-186, ArrayletMin.hs:191-192):
+ *   lam' = zipWith (+) orig_lam (foldRowsMatrixlet (+) ne')  =  L_j + (ne'[m1] + (ne'[m2] + ... + ne'[mk])) */
+static void vn_update_arraylet(const oracle_code *c, const double *L, const double *ne2, double *lam)
+{
+    for (int j = 0; j < c->N; j++) {
+        int q0 = c->col_ptr[j], q1 = c->col_ptr[j + 1];
+        if (q1 == q0) { lam[j] = L[j]; continue; }       /* (no fixture has an empty column) */
+        double acc = ne2[c->col_edge[q1 - 1]];
+        for (int q = q1 - 2; q >= q0; q--) acc = ne2[c->col_edge[q]] + acc;
+        lam[j] = L[j] + acc;
+    }
+}
+
 /* Same results as cn_update_literal for min-sum (up to the sign of an exact zero) in O(d):
  * the two-minimum + sign-parity form sketched in Model.hs:326-343 (decoder8) and Utils.hs:120-144. */
 static void cn_update_minsum_twomin(const oracle_code *c, const double *lam, const double *ne, double *ne2)
@@ -163,7 +210,8 @@ static void vn_update(const oracle_code *c, const double *L, const double *ne2, 
 /* The driver loop: Orig.hs:58-71 == Min.hs:54-67.
  *   loop n ne lam | syndrome ok -> lam | n >= maxIterations -> orig_lam | otherwise -> next
  *   result = map hard (...)
- * algo: 0 = sum-product (Orig.hs), 1 = normalised min-sum alpha=3/4 (Min.hs).
+ * algo: 0 = sum-product (Orig.hs), 1 = normalised min-sum alpha=3/4 (Min.hs),
+ *       2 = sum-product with the cached row product of Fast/CachedMult.hs (same loop, CachedMult.hs:233-243).
  * variant: 0 = literal O(d^2) check update, 1 = two-min O(d) (min-sum only).
  * trace_c2v (max_iters*E) / trace_lam (max_iters*N): after iteration t (0-based) the new messages /
  * posteriors are stored at offset t; may be NULL.
@@ -181,9 +229,11 @@ int oracle_decode(const oracle_code *c, int algo, int variant, int max_iters, co
         ok = syndrome_ok(c, lam);
         if (ok) break;
         if (n >= max_iters) break;
-        if (algo == 1 && variant == 1) cn_update_minsum_twomin(c, lam, ne, ne2);
+        if (algo == 2) cn_update_cached_mult(c, lam, ne, ne2);
+        else if (algo == 1 && variant == 1) cn_update_minsum_twomin(c, lam, ne, ne2);
         else cn_update_literal(c, algo, lam, ne, ne2);
-        vn_update(c, llr, ne2, lam);
+        if (algo == 2) vn_update_arraylet(c, llr, ne2, lam);
+        else vn_update(c, llr, ne2, lam);
         if (trace_c2v) memcpy(trace_c2v + (size_t)n * E, ne2, sizeof(double) * E);
         if (trace_lam) memcpy(trace_lam + (size_t)n * N, lam, sizeof(double) * N);
         double *t = ne; ne = ne2; ne2 = t;

@@ -42,7 +42,7 @@ def lib():
     return _lib
 
 
-ALGO = {"spa": 0, "min": 1, "minsum": 1, 0: 0, 1: 1}
+ALGO = {"spa": 0, "min": 1, "minsum": 1, "spa_cm": 2, "cm": 2, 0: 0, 1: 1, 2: 2}
 
 
 class Oracle:

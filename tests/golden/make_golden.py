@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Generates tests/golden/*.npz with oracle/dense_ref.py, the literal dense transcription of
-Reference/Orig.hs:58-98 and Reference/Min.hs:54-104.
+Reference/Orig.hs:58-98 and Reference/Min.hs:54-104 (and, algo "cm", of Fast/CachedMult.hs:233-264).
 
 The reference itself cannot run here (no GHC; ecc-manifold absent), so these are NOT reference outputs:
 they pin the C oracle and the CUDA kernels to a second, independently written statement of the same
@@ -73,7 +73,7 @@ def make(code_name, algo, ebn0_db, max_iters, n_frames, seed, n_tx=None, keep="a
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["moon", "jpl1024", "mackay", "jpl4096"]
+    which = sys.argv[1:] or ["moon", "jpl1024", "mackay", "jpl4096", "cm"]
     if "moon" in which:
         make("moon.7.13", "spa", 2.0, 20, 48, 11)
         make("moon.7.13", "min", 2.0, 20, 48, 12)
@@ -87,3 +87,6 @@ if __name__ == "__main__":
     if "jpl4096" in which:
         make("jpl.4096.4.5", "min", 4.0, 10, 2, 41, n_tx=5120, keep="ends")
         make("jpl.4096.4.5", "spa", 3.6, 6, 1, 42, n_tx=5120, keep="ends")
+    if "cm" in which:   # the cached-product sum-product of Fast/CachedMult.hs:233-264 (dense_ref.ldpc_cached_mult)
+        make("moon.7.13", "cm", 2.0, 20, 24, 14)
+        make("jpl.1024.4.5", "cm", 3.9, 8, 2, 23, n_tx=1280, keep="ends")

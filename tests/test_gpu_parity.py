@@ -452,3 +452,35 @@ def test_simulate_multi_single_process(gpu_lib, dcodes, builtin_codes):
     gpu_lib.load().ldpc_b200_simulate_multi_release()
     with pytest.raises(gpu_lib.LdpcError):
         gpu_lib.simulate_multi(dcodes["jpl.1024.4.5"], n_dev + 1, "min", "fp32", 512, 20, 3.4, code.K, 1280, 9, 0, 10)
+
+
+def test_cached_mult_variant(gpu_lib, dcodes, builtin_codes, oracles):
+    """the cached-product sum-product of Fast/CachedMult.hs:233-264 (float64, STREAM engine) against
+    the oracle's restatement: decisions / iteration counts on a batch, per-edge messages of single frames."""
+    for name in ("moon.7.13", "jpl.1024.4.5", "jpl.4096.4.5"):
+        code = builtin_codes[name]
+        F = 400 if name == "moon.7.13" else 48
+        llr = awgn_llrs(code, EBN0[name], F, 4242, TX[name])
+        dec = gpu_lib.Decoder(dcodes[name], "spa_cm", "fp64", max_batch=64)
+        assert dec.engine() == gpu_lib.ENGINE_STREAM
+        bits, iters, conv = dec.decode(llr, 12)
+        rb, ri, rc = oracles[name].decode_batch("spa_cm", 12, llr)
+        assert (bits == rb).all(axis=1).mean() >= 0.999 and (iters == ri).mean() >= 0.99
+        for f in range(2):
+            b, it, cv, c2v, lam = dec.decode_trace(llr[f], 12)
+            ob, oit, ocv, oc2v, olam = oracles[name].decode("spa_cm", 12, llr[f], trace=True)
+            assert it == oit and cv == ocv and np.array_equal(b, ob)
+            if it:
+                assert spa_close(c2v[0], oc2v[0]) and spa_close(lam[0], olam[0])
+                assert spa_close(c2v[-1], oc2v[-1]) and spa_close(lam[-1], olam[-1])
+        dec.close()
+    with pytest.raises(gpu_lib.LdpcError):          # float64-only variant: fails loudly instead of silently switching
+        gpu_lib.Decoder(dcodes["moon.7.13"], "spa_cm", "fp32", max_batch=8)
+    from ecc_ldpc_b200 import ecc
+    (e,) = ecc.match("ldpc/b200-spa-cm-fp64/jpl.1024.4.5/10/4/5", max_batch=8)
+    assert e.name == "ldpc/b200-spa-cm-fp64/jpl.1024.4.5/10/4/5"
+    rx = awgn_llrs(builtin_codes["jpl.1024.4.5"], 4.2, 4, 5, 1280)[:, :1280]
+    out, flags = e.decode_batch(rx)
+    for f in range(4):
+        ob, oflag, oit, ocv = oracles["jpl.1024.4.5"].ecc_decode("spa_cm", 10, 1024, 1280, rx[f])
+        assert np.array_equal(out[f], ob) and flags[f] == 1

@@ -266,3 +266,31 @@ def test_ber_line_format():
     from ecc_ldpc_b200 import lib
     line = lib.ber_line(39.70, "ldpc/model/jpl.1K/200", 0.0, 256, 29891, 1024)
     assert line == "39.70 ldpc/model/jpl.1K/200 0.0 256 29891 1.14e-1 +1% -1% 95%"
+
+
+def test_cached_mult_statedness(builtin_codes, oracles):
+    """Fast/CachedMult.hs (`ldpc/arraylet-cm`): the StableDiv row product divided by the own term is the leave-one-out
+    product of Orig.hs up to rounding, so decisions and iteration counts agree with the plain sum-product and the
+    messages differ only in the last digits; a valid codeword is a fixed point at iteration 0; the fallback rule holds."""
+    for name, ebn0, n_tx, iters in (("moon.7.13", 3.0, None, 20), ("jpl.1024.4.5", 3.9, 1280, 10)):
+        code, o = builtin_codes[name], oracles[name]
+        llr = awgn_llrs(code, ebn0, 12, 99, n_tx)
+        agree = 0
+        for f in range(llr.shape[0]):
+            a = o.decode("spa", iters, llr[f], trace=True)
+            b = o.decode("spa_cm", iters, llr[f], trace=True)
+            agree += int(np.array_equal(a[0], b[0]) and a[1] == b[1])
+            n = min(a[1], b[1], 2)
+            if n:
+                # first iterations: same quantity computed two ways (|msg| <= 12: away from the atanh' clamp)
+                m = np.abs(a[3][:n]) <= 12
+                assert np.allclose(a[3][:n][m], b[3][:n][m], rtol=1e-9, atol=1e-12)
+        assert agree >= llr.shape[0] - 1
+        cw = np.zeros(code.N)
+        bits, it, cv = o.decode("spa_cm", 5, 3.0 * (2.0 * cw - 1.0))
+        assert it == 0 and cv and not bits.any()
+    code, o = builtin_codes["jpl.1024.4.5"], oracles["jpl.1024.4.5"]
+    llr = awgn_llrs(code, 1.0, 2, 3, 1280)                     # hopeless SNR: never converges in 3 iterations
+    for f in range(2):
+        bits, it, cv = o.decode("spa_cm", 3, llr[f])
+        assert it == 3 and not cv and np.array_equal(bits, (llr[f] > 0).astype(np.uint8))     # hard(orig_lam)
