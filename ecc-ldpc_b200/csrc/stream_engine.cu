@@ -306,19 +306,23 @@ __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restri
     if (tid == 0) mbar_init(&bar, 1);
     const bool idle = f >= F || (skip_done && state[f]);
     if (!__syncthreads_or(!idle)) return;                                   // every frame of the block has stopped
-    // producers: thread 0 fetches the posterior rows, thread 32 the message rows.  (Spreading the issue over all four
-    // warps was measured 25 % SLOWER: the copies of one thread pipeline well, and the other warps are better left idle.)
+    // producers: the lanes of warp 0 fetch the posterior rows, the lanes of warp 1 the message rows -- lane q owns copy q,
+    // so the address arithmetic runs across the lanes and only the (warp-level) copy instruction itself is serialised.
+    // (Spreading the copies over all four warps was measured 25 % slower.)
     if (tid == 0) {
         uint32_t rows = 0;
         for (int c = 0; c < nchk; c++) rows += (uint32_t)s_rec[c * S + 1];
         mbar_expect_tx(&bar, 2u * rows * ROW);
-        for (int c = 0; c < nchk; c++)
-            for (int k = 0; k < s_rec[c * S + 1]; k++)
-                bulk_g2s(lam_s[c * MAXD + k], lam + (size_t)s_rec[c * S + 2 + k] * Bp + f0, ROW, &bar);
-    } else if (tid == 32) {
-        for (int c = 0; c < nchk; c++)
-            for (int k = 0; k < s_rec[c * S + 1]; k++)
-                bulk_g2s(ne_s[c * MAXD + k], ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ROW, &bar);
+    }
+    if (tid < 64) {
+        const int q = tid & 31;
+        for (int i = q; i < nchk * MAXD; i += 32) {
+            const int c = i / MAXD, k = i % MAXD;
+            if (k < s_rec[c * S + 1]) {
+                if (tid < 32) bulk_g2s(lam_s[i], lam + (size_t)s_rec[c * S + 2 + k] * Bp + f0, ROW, &bar);
+                else bulk_g2s(ne_s[i], ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ROW, &bar);
+            }
+        }
     }
     mbar_wait(&bar, 0);
     int par_any = 0;
@@ -368,11 +372,13 @@ __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restri
     // Frames of this block that have already stopped get their (never used again) messages overwritten too.
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
-        for (int c = 0; c < nchk; c++)
-            for (int k = 0; k < s_rec[c * S + 1]; k++)
-                bulk_s2g(ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ne_s[c * MAXD + k], ROW);
-        bulk_commit_wait_read();
+    if (tid < 32) {
+        bool any = false;
+        for (int i = tid; i < nchk * MAXD; i += 32) {
+            const int c = i / MAXD, k = i % MAXD;
+            if (k < s_rec[c * S + 1]) { bulk_s2g(ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ne_s[i], ROW); any = true; }
+        }
+        if (any) bulk_commit_wait_read();
     }
 }
 
@@ -400,11 +406,13 @@ __global__ void __launch_bounds__(TPB) k_vn_tma(DeviceGraph g, const T *__restri
         uint32_t n = 0;
         for (int v = 0; v < nvar; v++) n += 1u + (uint32_t)s_rec[v * S];
         mbar_expect_tx(&bar, n * ROW);
-        for (int v = 0; v < nvar; v++) bulk_g2s(rows[v * R], L + (size_t)(j0 + v) * Bp + f0, ROW, &bar);
-    } else if (tid == 32) {
-        for (int v = 0; v < nvar; v++)
-            for (int i = 0; i < s_rec[v * S]; i++)
-                bulk_g2s(rows[v * R + 1 + i], ne + (size_t)s_rec[v * S + 1 + i] * Bp + f0, ROW, &bar);
+    }
+    if (tid < 64) {                                                         // lane q of warps 0 / 1 owns copy q (see k_cn_tma)
+        for (int i = tid; i < nvar * R; i += 64) {
+            const int v = i / R, r = i % R;
+            if (r == 0) bulk_g2s(rows[i], L + (size_t)(j0 + v) * Bp + f0, ROW, &bar);
+            else if (r - 1 < s_rec[v * S]) bulk_g2s(rows[i], ne + (size_t)s_rec[v * S + r] * Bp + f0, ROW, &bar);
+        }
     }
     mbar_wait(&bar, 0);
     for (int v = 0; v < nvar; v++) {
@@ -417,8 +425,8 @@ __global__ void __launch_bounds__(TPB) k_vn_tma(DeviceGraph g, const T *__restri
     // (frames of this block that have already stopped get a posterior they never read again)
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
-        for (int v = 0; v < nvar; v++) bulk_s2g(lam + (size_t)(j0 + v) * Bp + f0, rows[v * R], ROW);
+    if (tid < nvar) {
+        bulk_s2g(lam + (size_t)(j0 + tid) * Bp + f0, rows[tid * R], ROW);
         bulk_commit_wait_read();
     }
 }
