@@ -287,6 +287,56 @@ __device__ __forceinline__ void bulk_commit_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One check row of one frame from / to the staged rows in shared memory; returns the syndrome parity of the row.
+// FULL: the row has exactly MAXD edges (no masks); otherwise it is padded to MAXD with the neutral element of the check
+// operator, so both forms use the same predicate-free leave-one-out tree as the RESIDENT engine (~2.6 operations per edge).
+template <typename T, int ALGO, int MAXD, bool FULL>
+__device__ __forceinline__ int cn_row(T (*lam_r)[TPB], T (*ne_r)[TPB], int tid, int d)
+{
+    T x[MAXD];
+    int par = 0;
+#pragma unroll
+    for (int k = 0; k < MAXD; k++) {
+        const T l = lam_r[k][tid], n = ne_r[k][tid];                        // rows >= d: stale shared memory, masked below
+        if (FULL) {
+            par ^= (l > (T)0);                                              // syndrome of the CURRENT posteriors (Orig.hs:73-78)
+            x[k] = -Num<T>::sub(l, n);                                      // x_j = -(lam_j - ne[m,j])   (Min.hs:80 / Orig.hs:84)
+        } else {
+            par ^= (k < d) & (l > (T)0);
+            x[k] = (k < d) ? -Num<T>::sub(l, n) : Num<T>::inf();
+        }
+    }
+    if constexpr (ALGO == LDPC_B200_ALGO_SPA) {
+        // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) (pad: x = +inf -> c = 0, the
+        // identity) combined leave-one-out in the tree; the sign of x_j rides in the sign bit of its complement;
+        // magnitude lg2((2-c)/c) capped at the reference's clamp and signed by one FMNMX.XORSIGN; times ln 2.
+        uint32_t sgn = 0;
+#pragma unroll
+        for (int k = 0; k < MAXD; k++) sgn ^= __float_as_uint((float)x[k]);
+        const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
+        float leaf[MAXD];
+#pragma unroll
+        for (int k = 0; k < MAXD; k++)
+            leaf[k] = __uint_as_float(__float_as_uint(spa_compl((float)x[k])) | (__float_as_uint((float)x[k]) & 0x80000000u));
+        BoxTree<float, 0, MAXD, OpComplAbs> tree;
+        tree.build([&](auto ki) { return leaf[decltype(ki)::value]; });
+        tree.down_root([&](auto ki, float others) {
+            constexpr int k = decltype(ki)::value;
+            const float w = FB<float>::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(leaf[k]) & 0x80000000u)));
+            if (FULL || k < d) ne_r[k][tid] = (T)(w * 0.69314718055994531f);
+        });
+    } else {
+        // Min.hs:79-89: ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]; min' is exact and associative, pad = +inf
+        BoxTree<T, 0, MAXD> tree;
+        tree.build([&](auto ki) { return x[decltype(ki)::value]; });
+        tree.down_root([&](auto ki, T others) {
+            constexpr int k = decltype(ki)::value;
+            if (FULL || k < d) ne_r[k][tid] = Num<T>::mul((T)-0.75, others);
+        });
+    }
+    return par;
+}
+
 // Check-node update: CTA = CPC consecutive checks x TPB frames; thread = one frame, loops over the CPC checks.
 template <typename T, int ALGO, int MAXD, int CPC>
 __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ ne,
@@ -328,45 +378,10 @@ __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restri
     int par_any = 0;
     for (int c = 0; c < nchk; c++) {
         const int d = s_rec[c * S + 1];
-        // The row is padded to MAXD with the neutral element of the check operator, so the update is the same
-        // predicate-free leave-one-out tree as in the RESIDENT engine (~2.6 operations per edge).
-        T x[MAXD];
-        int par = 0;
-#pragma unroll
-        for (int k = 0; k < MAXD; k++) {
-            const T l = lam_s[c * MAXD + k][tid], n = ne_s[c * MAXD + k][tid];   // rows >= d: stale shared memory, masked below
-            par ^= (k < d) & (l > (T)0);                                        // syndrome of the CURRENT posteriors (Orig.hs:73-78)
-            x[k] = (k < d) ? -Num<T>::sub(l, n) : Num<T>::inf();                // x_j = -(lam_j - ne[m,j])   (Min.hs:80 / Orig.hs:84)
-        }
-        par_any |= par;
-        if constexpr (ALGO == LDPC_B200_ALGO_SPA) {
-            // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) (pad: x = +inf -> c = 0, the
-            // identity) combined leave-one-out in the tree; the sign of x_j rides in the sign bit of its complement;
-            // magnitude lg2((2-c)/c) capped at the reference's clamp and signed by one FMNMX.XORSIGN; times ln 2.
-            uint32_t sgn = 0;
-#pragma unroll
-            for (int k = 0; k < MAXD; k++) sgn ^= __float_as_uint((float)x[k]);
-            const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
-            float leaf[MAXD];
-#pragma unroll
-            for (int k = 0; k < MAXD; k++)
-                leaf[k] = __uint_as_float(__float_as_uint(spa_compl((float)x[k])) | (__float_as_uint((float)x[k]) & 0x80000000u));
-            BoxTree<float, 0, MAXD, OpComplAbs> tree;
-            tree.build([&](auto ki) { return leaf[decltype(ki)::value]; });
-            tree.down_root([&](auto ki, float others) {
-                constexpr int k = decltype(ki)::value;
-                const float w = FB<float>::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(leaf[k]) & 0x80000000u)));
-                if (k < d) ne_s[c * MAXD + k][tid] = (T)(w * 0.69314718055994531f);
-            });
-        } else {
-            // Min.hs:79-89: ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]; min' is exact and associative, pad = +inf
-            BoxTree<T, 0, MAXD> tree;
-            tree.build([&](auto ki) { return x[decltype(ki)::value]; });
-            tree.down_root([&](auto ki, T others) {
-                constexpr int k = decltype(ki)::value;
-                if (k < d) ne_s[c * MAXD + k][tid] = Num<T>::mul((T)-0.75, others);
-            });
-        }
+        // rows of the full class degree (all rows of a regular code, the degree-18 rows of the AR4JA codes) take the
+        // mask-free instance; the others are padded to MAXD with the neutral element
+        if (d == MAXD) par_any |= cn_row<T, ALGO, MAXD, true>(lam_s + c * MAXD, ne_s + c * MAXD, tid, d);
+        else par_any |= cn_row<T, ALGO, MAXD, false>(lam_s + c * MAXD, ne_s + c * MAXD, tid, d);
     }
     if (par_any && !idle) unsat[f] = 1;                                     // k_status reads it after this kernel
     // Frames of this block that have already stopped get their (never used again) messages overwritten too.
