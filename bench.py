@@ -346,6 +346,44 @@ def main():
         extra["ebn0_4.0_no_early_exit"] = {"info_gbit_per_s": f * code.K / 1e9, "frames_per_s": f, "avg_iters": float(MAX_ITERS),
                                            "edge_updates_per_s": f * MAX_ITERS * code.E}
 
+        # ---- the other BASELINE.json configurations and engines, device-resident, kernel-timed (rank 0 only) ----
+        if rank == 0:
+            def run_cfg(code_name, algo, engine_id, frames, max_it, ebn0, n_tx, reps=3):
+                c2 = code if code_name == CODE else codes.load_builtin(code_name)
+                dc2 = dcode if code_name == CODE else lib.DeviceCode(c2)
+                de2 = lib.Decoder(dc2, algo, "fp32", max_batch=frames, engine=engine_id)
+                W2 = (c2.N + 31) // 32
+                tl = torch.empty((frames, c2.N), dtype=torch.float32, device="cuda")
+                tb = torch.zeros((frames, W2), dtype=torch.int32, device="cuda")
+                ti = torch.zeros(frames, dtype=torch.int32, device="cuda")
+                tc = torch.zeros(frames, dtype=torch.uint8, device="cuda")
+                de2.generate_llr(tl.data_ptr(), ebn0, c2.K, n_tx, SEED, 0, frames); de2.sync()
+                ms = []
+                for _ in range(reps + 1):
+                    de2.decode_device(tl.data_ptr(), tb.data_ptr(), max_it, frames, early_exit=True, d_iters=ti.data_ptr(), d_conv=tc.data_ptr())
+                    de2.sync()
+                    ms.append(de2.last_timing()[0])
+                m = float(np.median(ms[1:]))
+                it = float(ti.float().mean().item())
+                f = frames / (m * 1e-3)
+                out = {"engine": {1: "stream", 2: "resident"}[de2.engine()], "frames": frames, "max_iters": max_it, "ebn0_db": ebn0,
+                       "kernel_ms": m, "frames_per_s": f, "info_gbit_per_s": f * c2.K / 1e9, "avg_iters": it,
+                       "edge_updates_per_s": f * it * c2.E, "fer": float((tc == 0).float().mean().item())}
+                ba = it * 4 * (3 * c2.E + 3 * c2.N) + 4 * n_tx + c2.K // 8
+                out["alg_gb_per_s"] = f * ba / 1e9
+                out["hbm_frac"] = out["alg_gb_per_s"] / peak
+                de2.close()
+                return out
+            extra["spa_jpl4096_20it_worst"] = run_cfg(CODE, "spa", lib.ENGINE_AUTO, 16384, 20, EBN0_WORST, N_TX)
+            extra["spa_jpl4096_50it_3.5dB"] = run_cfg(CODE, "spa", lib.ENGINE_AUTO, 16384, 50, 3.5, N_TX)
+            extra["minsum_jpl4096_50it_3.5dB"] = run_cfg(CODE, "min", lib.ENGINE_AUTO, 32768, 50, 3.5, N_TX)
+            extra["minsum_jpl1024_20it_16k_worst"] = run_cfg("jpl.1024.4.5", "min", lib.ENGINE_AUTO, 16384, 20, EBN0_WORST, 1280)
+            extra["minsum_jpl1024_20it_16k_4.0dB"] = run_cfg("jpl.1024.4.5", "min", lib.ENGINE_AUTO, 16384, 20, 4.0, 1280)
+            # the HBM-streaming engine (any H): the kernel whose roofline IS the HBM roof
+            extra["stream_minsum_jpl4096_20it_worst"] = run_cfg(CODE, "min", lib.ENGINE_STREAM, 8192, 20, EBN0_WORST, N_TX)
+            extra["stream_spa_jpl4096_20it_worst"] = run_cfg(CODE, "spa", lib.ENGINE_STREAM, 8192, 20, EBN0_WORST, N_TX)
+            extra["stream_minsum_1920.1280.3.303_20it_worst"] = run_cfg("1920.1280.3.303", "min", lib.ENGINE_STREAM, 32768, 20, 0.0, 1920)
+
     # ---------------- CPU baseline beside it (rank 0, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
