@@ -7,6 +7,11 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <new>
 
 namespace ldpc {
@@ -331,6 +336,7 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
         ldpc_b200_decoder::PipeSet &s = d->pipe[k];
         if (k == 1) { cudaFree(s.d_in); cudaFree(s.d_bits); cudaFree(s.d_iters); cudaFree(s.d_conv); }
         cudaFree(s.d_bytes);
+        if (s.h_conv) cudaFreeHost(s.h_conv);
         if (s.h2d_done) { cudaEventDestroy(s.h2d_done); cudaEventDestroy(s.d2h_done); cudaEventDestroy(s.t0); cudaEventDestroy(s.t1); }
     }
     if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
@@ -373,6 +379,86 @@ int ldpc_b200_decode_device(ldpc_b200_decoder_t *d, int max_iters, int early_exi
                          d_iters ? d_iters : d->d_iters, d_converged ? d_converged : d->d_conv);
     end_timing(d);
     return rc;
+}
+
+// ---- host-side narrowing of float64 LLRs (fp32 decoders) -------------------------------------------------------
+// The reference hands the decoder `U.Vector Double` (Utils.hs:68); the production kernels compute in float32.  The
+// host->device hop is the bottleneck of the host-buffer calls (PCIe, ~50 GB/s), so the doubles are rounded to float
+// (round-to-nearest, the same conversion the device would do) by a small pool of host threads into pinned staging
+// and only 4 bytes per LLR cross PCIe.  OPT-IN (LDPC_B200_HOST_NARROW=1): on the 16-vCPU host of the B200 boxes the
+// narrowing itself runs at ~36 GB/s of input and the call got SLOWER (3.6 vs 4.9 Gbit/s for jpl.4096.4.5, 8 threads:
+// 4.0), so the default keeps the doubles on PCIe and converts on the device; hosts with more memory bandwidth per GPU
+// can turn it on.
+class HostPool {
+public:
+    static HostPool &get() { static HostPool p; return p; }
+    int size() const { return (int)workers_.size(); }
+    // runs fn(part, nparts) on every worker and returns when all are done
+    void run(const std::function<void(int, int)> &fn)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &fn; pending_ = (int)workers_.size(); gen_++;
+        cv_.notify_all();
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    HostPool()
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = (int)std::min<unsigned>(hc ? hc : 4, 16);
+        if (const char *e = getenv("LDPC_B200_HOST_THREADS")) n = std::max(1, atoi(e));
+        for (int i = 0; i < n; i++) workers_.emplace_back([this, i, n] { loop(i, n); });
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void loop(int i, int n)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)> *fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            if (fn) (*fn)(i, n);
+            { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_all(); }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+static bool host_narrow_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("LDPC_B200_HOST_NARROW"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+
+// dst[f][0..take) = (float)src[f*stride + 0..take), rows of `take` floats packed back to back
+static void narrow_rows(const double *src, size_t stride, int take, int F, float *dst)
+{
+    HostPool::get().run([&](int part, int nparts) {
+        int f0 = (int)((int64_t)F * part / nparts), f1 = (int)((int64_t)F * (part + 1) / nparts);
+        for (int f = f0; f < f1; f++) {
+            const double *in = src + (size_t)f * stride;
+            float *out = dst + (size_t)f * take;
+            for (int j = 0; j < take; j++) out[j] = (float)in[j];
+        }
+    });
 }
 
 static const int PIPE_CHUNK_MAX = 4096;
@@ -425,6 +511,8 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
     int cap = d->pipe[0].frames;
     int chunk = std::max(256, (n_frames + 3) / 4);
     chunk = std::min(chunk, cap);
+    // float64 in, float32 decoder: round on the host, ship half the bytes (large batches only: the pool has a wake-up cost)
+    const bool narrow = is_double && d->precision == LDPC_B200_PREC_FP32 && n_frames >= 64 && host_narrow_enabled();
     double total_ms = 0.0;
     int64_t total_launches = 0;
     auto harvest = [&](ldpc_b200_decoder::PipeSet &s) -> int {
@@ -442,7 +530,17 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         ldpc_b200_decoder::PipeSet &s = d->pipe[k & 1];
         rc = harvest(s);                         // also guarantees the set's buffers are free again
         if (rc) break;
-        if (in_take > 0 && (in_take < N || in_stride != N)) {
+        bool dev_double = is_double;
+        if (narrow) {
+            // chunk k is narrowed while chunk k-1 decodes and its H2D copy runs (the calls below are asynchronous)
+            if (!s.h_conv) LDPC_CUDA(cudaHostAlloc((void **)&s.h_conv, (size_t)s.frames * N * sizeof(float), cudaHostAllocDefault));
+            const int take = in_take > 0 ? in_take : N;
+            const size_t stride = in_take > 0 ? (size_t)in_stride : (size_t)N;
+            narrow_rows((const double *)llr + (size_t)f0 * stride, stride, take, F, s.h_conv);
+            if (take < N) LDPC_CUDA(cudaMemset2DAsync((char *)s.d_in + (size_t)take * 4, (size_t)N * 4, 0, (size_t)(N - take) * 4, F, d->copy_stream));
+            LDPC_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)N * 4, s.h_conv, (size_t)take * 4, (size_t)take * 4, F, cudaMemcpyHostToDevice, d->copy_stream));
+            dev_double = false;
+        } else if (in_take > 0 && (in_take < N || in_stride != N)) {
             if (in_take < N)
                 LDPC_CUDA(cudaMemset2DAsync((char *)s.d_in + (size_t)in_take * in_es, (size_t)N * in_es, 0, (size_t)(N - in_take) * in_es, F, d->copy_stream));
             LDPC_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)N * in_es, (const char *)llr + (size_t)f0 * in_stride * in_es, (size_t)in_stride * in_es,
@@ -454,7 +552,7 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         LDPC_CUDA(cudaStreamWaitEvent(d->stream, s.h2d_done, 0));
         d->launches = 0;
         LDPC_CUDA(cudaEventRecord(s.t0, d->stream));
-        rc = decode_dispatch(d, max_iters, 1, F, s.d_in, is_double, s.d_bits, s.d_iters, s.d_conv);
+        rc = decode_dispatch(d, max_iters, 1, F, s.d_in, dev_double, s.d_bits, s.d_iters, s.d_conv);
         if (!rc && bits_bytes) rc = unpack_bits(d, F, s.d_bits, s.d_bytes);
         if (rc) break;
         LDPC_CUDA(cudaEventRecord(s.t1, d->stream));

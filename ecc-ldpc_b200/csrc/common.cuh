@@ -85,6 +85,7 @@ struct ldpc_b200_decoder {
         void *d_in = nullptr; uint32_t *d_bits = nullptr; uint8_t *d_bytes = nullptr;
         int32_t *d_iters = nullptr; uint8_t *d_conv = nullptr;
         cudaEvent_t h2d_done = nullptr, t0 = nullptr, t1 = nullptr, d2h_done = nullptr;
+        float *h_conv = nullptr;     // pinned [frames][N] float: float64 LLRs narrowed on the host in front of the PCIe hop
         int frames = 0;              // capacity in frames
         bool timing_pending = false;
     } pipe[2];
