@@ -366,7 +366,7 @@ def main():
                 m = float(np.median(ms[1:]))
                 it = float(ti.float().mean().item())
                 f = frames / (m * 1e-3)
-                out = {"engine": {1: "stream", 2: "resident"}[de2.engine()], "frames": frames, "max_iters": max_it, "ebn0_db": ebn0,
+                out = {"engine": {1: "stream", 2: "resident", 3: "onchip"}[de2.engine()], "frames": frames, "max_iters": max_it, "ebn0_db": ebn0,
                        "kernel_ms": m, "frames_per_s": f, "info_gbit_per_s": f * c2.K / 1e9, "avg_iters": it,
                        "edge_updates_per_s": f * it * c2.E, "fer": float((tc == 0).float().mean().item())}
                 ba = it * 4 * (3 * c2.E + 3 * c2.N) + 4 * n_tx + c2.K // 8
@@ -411,7 +411,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
-                       "frames_per_step_per_gpu": B, "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident"}[dec.engine()],
+                       "frames_per_step_per_gpu": B, "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident", 3: "onchip"}[dec.engine()],
                        "l2": "inputs larger than L2 (%.0f MB of LLRs per step per GPU)" % (B * code.N * 4 / 1e6),
                        "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step",
                        "numa_node_rank0": numa},

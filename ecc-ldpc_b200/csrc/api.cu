@@ -85,6 +85,38 @@ static int upload_graph(ldpc_b200_code *c)
         }
         LDPC_CUDA(cudaMalloc(&g.col_ell, sizeof(int32_t) * t.size()));
         LDPC_CUDA(cudaMemcpy(g.col_ell, t.data(), sizeof(int32_t) * t.size(), cudaMemcpyHostToDevice));
+        if (g.row_ell_d && c->E > 0) {
+            // slot of edge e = (its check) * DP + (its position in the check's row)
+            const int DP = g.row_ell_d + 1;
+            std::vector<int32_t> slot_of_edge(c->E), cs(c->E), ts((size_t)c->N * S, 0);
+            for (int m = 0; m < c->M; m++)
+                for (int e = c->row_ptr[m]; e < c->row_ptr[m + 1]; e++) slot_of_edge[e] = m * DP + (e - c->row_ptr[m]);
+            for (int q = 0; q < c->E; q++) cs[q] = slot_of_edge[c->col_edge[q]];
+            for (int j = 0; j < c->N; j++) {
+                int d = t[(size_t)j * S];
+                ts[(size_t)j * S] = d;
+                for (int k = 0; k < D; k++) ts[(size_t)j * S + 1 + k] = d > 0 ? slot_of_edge[t[(size_t)j * S + 1 + k]] : 0;
+            }
+            LDPC_CUDA(cudaMalloc(&g.col_slot_ell, sizeof(int32_t) * ts.size()));
+            LDPC_CUDA(cudaMemcpy(g.col_slot_ell, ts.data(), sizeof(int32_t) * ts.size(), cudaMemcpyHostToDevice));
+            LDPC_CUDA(cudaMalloc(&g.col_slot, sizeof(int32_t) * cs.size()));
+            LDPC_CUDA(cudaMemcpy(g.col_slot, cs.data(), sizeof(int32_t) * cs.size(), cudaMemcpyHostToDevice));
+            // transposed copies
+            std::vector<int32_t> ra((size_t)(g.row_ell_d + 1) * c->M), ca((size_t)S * c->N);
+            g.row_regular = 1;
+            for (int m = 0; m < c->M; m++) {
+                int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
+                if (d != g.row_ell_d) g.row_regular = 0;
+                ra[m] = d;
+                for (int k = 0; k < g.row_ell_d; k++) ra[(size_t)(1 + k) * c->M + m] = d > 0 ? c->col_idx[b + (k < d ? k : d - 1)] : 0;
+            }
+            for (int j = 0; j < c->N; j++)
+                for (int k = 0; k < S; k++) ca[(size_t)k * c->N + j] = ts[(size_t)j * S + k];
+            LDPC_CUDA(cudaMalloc(&g.row_soa, sizeof(int32_t) * ra.size()));
+            LDPC_CUDA(cudaMemcpy(g.row_soa, ra.data(), sizeof(int32_t) * ra.size(), cudaMemcpyHostToDevice));
+            LDPC_CUDA(cudaMalloc(&g.col_soa, sizeof(int32_t) * ca.size()));
+            LDPC_CUDA(cudaMemcpy(g.col_soa, ca.data(), sizeof(int32_t) * ca.size(), cudaMemcpyHostToDevice));
+        }
     }
     return 0;
 }
@@ -235,6 +267,7 @@ int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_
     LDPC_CUDA(cudaGetDevice(&c->device));        // the code lives on the CURRENT device (multi-GPU hosts switch devices)
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }
+    if (onchip_fits(c, LDPC_B200_PREC_FP32)) c->resident_kind = 3;      // run-time table on-chip kernel
     *out = c;
     return 0;
 }
@@ -267,6 +300,7 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
     c->resident_kind = resident_kind_for(c);
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }
+    if (!c->resident_kind && onchip_fits(c, LDPC_B200_PREC_FP32)) c->resident_kind = 3;
     *out = c;
     return 0;
 }
@@ -275,7 +309,7 @@ void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
 {
     if (!c) return;
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
-    cudaFree(c->g.row_ell); cudaFree(c->g.col_ell);
+    cudaFree(c->g.row_ell); cudaFree(c->g.col_ell); cudaFree(c->g.col_slot_ell); cudaFree(c->g.col_slot); cudaFree(c->g.row_soa); cudaFree(c->g.col_soa);
     delete c;
 }
 
@@ -314,16 +348,27 @@ int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precisi
 
 int ldpc_b200_decoder_set_engine(ldpc_b200_decoder_t *d, int engine)
 {
-    if (!d || engine < 0 || engine > 2) { set_error("set_engine: bad arguments"); return LDPC_B200_EINVAL; }
-    if (engine == LDPC_B200_ENGINE_RESIDENT && !resident_supports(d)) {
-        set_error("RESIDENT engine has no specialisation for this code / algorithm / precision");
+    if (!d || engine < 0 || engine > 3) { set_error("set_engine: bad arguments"); return LDPC_B200_EINVAL; }
+    if (engine == LDPC_B200_ENGINE_RESIDENT && d->code->resident_kind != 1 && d->code->resident_kind != 2) {
+        set_error("RESIDENT engine has no compiled specialisation for this code (ONCHIP is the run-time table form)");
         return LDPC_B200_EUNSUPPORTED;
     }
+    int prev = d->engine;
     d->engine = engine;
+    if ((engine == LDPC_B200_ENGINE_RESIDENT || engine == LDPC_B200_ENGINE_ONCHIP) && !resident_supports(d)) {
+        d->engine = prev;
+        set_error("no on-chip kernel for this code / algorithm / precision");
+        return LDPC_B200_EUNSUPPORTED;
+    }
     return 0;
 }
 
-int ldpc_b200_decoder_engine(const ldpc_b200_decoder_t *d) { return d ? pick_engine(d) : LDPC_B200_EINVAL; }
+int ldpc_b200_decoder_engine(const ldpc_b200_decoder_t *d)
+{
+    if (!d) return LDPC_B200_EINVAL;
+    int e = pick_engine(d);
+    return (e == LDPC_B200_ENGINE_RESIDENT && resident_kind_of(d) == 3) ? LDPC_B200_ENGINE_ONCHIP : e;
+}
 
 void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
 {

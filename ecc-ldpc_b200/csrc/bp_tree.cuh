@@ -25,6 +25,7 @@ template <> struct FB<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     // min' of Min.hs:89 in ONE instruction: FMNMX.XORSIGN = min(|a|,|b|) carrying sign(a) xor sign(b)
     static __device__ __forceinline__ float box(float a, float b)
     {
@@ -50,6 +51,7 @@ template <> struct FB<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static __device__ __forceinline__ double box(double a, double b)
     {
         return __longlong_as_double((long long)(bits(fmin(fabs(a), fabs(b))) | ((bits(a) ^ bits(b)) & SIGN)));
@@ -108,3 +110,35 @@ struct OpComplAbs { static __device__ __forceinline__ float f(float a, float b) 
 __device__ __forceinline__ float spa_mag_lg2(float c) { c = fabsf(c); return mufu_lg2(2.0f - c) - mufu_lg2(c); }
 #define SPA_CAP_LG2 54.0f   // 2 * 18.714973875118524 = ln((2 - 2^-53) / 2^-53) = 54 ln 2 to within 1e-16
 
+
+// One check row: x[0..MAXD) holds x_j = -(lam_j - ne[m,j]) for the row's d edges and the neutral element (+inf) in the
+// padding slots k >= d (FULL: d == MAXD, no padding); emit(k, ne'[m,k]) is called for every slot, the caller drops
+// k >= d.  Min-sum: ne' = (-3/4) * foldr1 min' [ x_j | j /= n ] (Min.hs:79-89; min' is exact and associative).
+// Sum-product (fp32 production form, see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) (pad: x = +inf -> c = 0, the
+// identity) combined leave-one-out in the tree; the sign of x_j rides in the sign bit of its complement; magnitude
+// lg2((2-c)/c) capped at the reference's clamp and signed by one FMNMX.XORSIGN; times ln 2.
+template <typename T, int ALGO, int MAXD, class Emit>
+__device__ __forceinline__ void cn_row_core(const T (&x)[MAXD], Emit &&emit)
+{
+    if constexpr (ALGO == LDPC_B200_ALGO_SPA) {
+        uint32_t sgn = 0;
+#pragma unroll
+        for (int k = 0; k < MAXD; k++) sgn ^= __float_as_uint((float)x[k]);
+        const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
+        float leaf[MAXD];
+#pragma unroll
+        for (int k = 0; k < MAXD; k++)
+            leaf[k] = __uint_as_float(__float_as_uint(spa_compl((float)x[k])) | (__float_as_uint((float)x[k]) & 0x80000000u));
+        BoxTree<float, 0, MAXD, OpComplAbs> tree;
+        tree.build([&](auto ki) { return leaf[decltype(ki)::value]; });
+        tree.down_root([&](auto ki, float others) {
+            constexpr int k = decltype(ki)::value;
+            const float w = FB<float>::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(leaf[k]) & 0x80000000u)));
+            emit(ki, (T)(w * 0.69314718055994531f));
+        });
+    } else {
+        BoxTree<T, 0, MAXD> tree;
+        tree.build([&](auto ki) { return x[decltype(ki)::value]; });
+        tree.down_root([&](auto ki, T others) { emit(ki, FB<T>::mul((T)-0.75, others)); });
+    }
+}

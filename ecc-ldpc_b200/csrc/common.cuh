@@ -32,6 +32,14 @@ struct DeviceGraph {
     //                                 reference's right fold), first COL_ELL_D of them, last one repeated}
     int32_t *row_ell = nullptr, *col_ell = nullptr;
     int row_ell_d = 0;
+    // ONCHIP engine: the same per-variable records with message SLOTS (check m, position k -> m * (row_ell_d + 1) + k)
+    // instead of edge ids, and the slot of every edge in CSC order for variables of degree > COL_ELL_D
+    int32_t *col_slot_ell = nullptr, *col_slot = nullptr;
+    // the same records transposed (structure of arrays: entry k of all checks / variables is contiguous), so that the
+    // threads of consecutive checks / variables read one cache line per record entry:
+    //   row_soa [row_ell_d + 1][M] : {degree, columns...};  col_soa [COL_ELL_D + 1][N] : {degree, slots in fold order...}
+    int32_t *row_soa = nullptr, *col_soa = nullptr;
+    int row_regular = 0;          // every check has exactly row_ell_d edges
     static constexpr int COL_ELL_D = 8;
 };
 
@@ -46,7 +54,7 @@ struct ldpc_b200_code {
     std::vector<int32_t> shifts;
     int device = -1;
     ldpc::DeviceGraph g;          // device copy
-    int resident_kind = 0;        // 0 = none, else id of the compiled RESIDENT specialisation
+    int resident_kind = 0;        // 0 = none, 1 / 2 = compiled RESIDENT specialisation, 3 = run-time table ONCHIP kernel
 };
 
 namespace ldpc {
@@ -112,11 +120,17 @@ int stream_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_fra
 // ---- resident engine (resident_engine.cu) ----
 int resident_kind_for(const ldpc_b200_code *c);          // 0 if no specialisation matches
 bool resident_supports(const ldpc_b200_decoder *d);
+int resident_kind_of(const ldpc_b200_decoder *d);       // 1 / 2 compiled specialisation, 3 run-time table ONCHIP kernel
 int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
                     bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv);
 int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float sigma, float llr_scale,
                       int k_info, int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
                       uint64_t *d_counters);
+
+// ---- on-chip engine for arbitrary codes (onchip_engine.cu) ----
+bool onchip_fits(const ldpc_b200_code *c, int precision);
+struct ResidentParams;
+int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p);
 
 // ---- channel (channel.cu) ----
 int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_tx, uint64_t seed,

@@ -44,6 +44,7 @@ namespace ldpc {
 
 #include "qc_tables.inc"
 #include "bp_tree.cuh"
+#include "resident_common.cuh"
 
 // Two frames per thread, packed as an fp32 pair in one 64-bit register pair.  sm_100 has packed fp32 arithmetic
 // (FADD2 / FMUL2 / FFMA2 on register pairs), 64-bit shared-memory accesses move both frames' words in one
@@ -111,18 +112,6 @@ template <class C> struct QcMap {
     static constexpr int NEH = max_part_edges();
     static constexpr int N = C::BC * C::SZ;
 };
-
-__device__ __forceinline__ void bar_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ bool bar_or(int id, int nthreads, bool pred)
-{
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %3, 0;\n\tbarrier.red.or.pred q, %1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"(id), "r"(nthreads), "r"((int)pred) : "memory");
-    return r != 0;
-}
 
 // Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
 // BLK = SZ*sizeof(T) bytes and BLK-aligned, so only the low log2(BLK) bits rotate: one add + one bit-select.
@@ -367,25 +356,6 @@ __device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t 
         }
     });
 }
-
-struct ResidentParams {
-    const void *llr;               // [F][N] in T, or nullptr: generate on the fly (simulate)
-    uint32_t *bits;                // [F][N/32] or nullptr
-    int32_t *iters;                // [F] or nullptr
-    uint8_t *conv;                 // [F] or nullptr
-    unsigned long long *counters;  // 5 x u64 or nullptr
-    unsigned int *work;            // work counter (zeroed before launch)
-    unsigned int n_frames;
-    int max_iters, early_exit;
-    // simulate
-    float sigma, scale;
-    int n_tx, k_info;
-    unsigned long long seed, first_frame;
-};
-
-struct FrameCounters {
-    unsigned long long frames = 0, ferr = 0, berr = 0, iters = 0, unconv = 0;
-};
 
 // Decode of one frame by the threads of part H (the iteration loop is instantiated per part so that no dispatch
 // happens inside it; all parts execute the same sequence of named barriers).
@@ -687,11 +657,20 @@ int resident_kind_for(const ldpc_b200_code *c)
     return 0;
 }
 
+// which on-chip kernel serves this decoder: the compiled specialisation of its code, or (no specialisation, or the
+// ONCHIP engine asked for explicitly) the run-time table kernel of onchip_engine.cu
+int resident_kind_of(const ldpc_b200_decoder *d)
+{
+    return d->engine == LDPC_B200_ENGINE_ONCHIP ? 3 : d->code->resident_kind;
+}
+
 bool resident_supports(const ldpc_b200_decoder *d)
 {
     // min-sum: fp32 and fp64; sum-product: fp32 only (fp64 sum-product is the STREAM engine's literal form)
-    return d->code->resident_kind != 0 && d->algo != LDPC_B200_ALGO_SPA_CM &&
-           (d->algo == LDPC_B200_ALGO_MINSUM || d->precision == LDPC_B200_PREC_FP32);
+    if (d->algo == LDPC_B200_ALGO_SPA_CM) return false;
+    if (!(d->algo == LDPC_B200_ALGO_MINSUM || d->precision == LDPC_B200_PREC_FP32)) return false;
+    if (resident_kind_of(d) == 3) return onchip_fits(d->code, d->precision);
+    return d->code->resident_kind != 0;
 }
 
 template <typename T>
@@ -767,9 +746,10 @@ static int launch_pair(ldpc_b200_decoder *d, ResidentParams &p)
 template <typename T, int ALGO>
 static int launch_kind(ldpc_b200_decoder *d, ResidentParams &p)
 {
-    switch (d->code->resident_kind) {
+    switch (resident_kind_of(d)) {
     case 1: return launch<QcJpl1024, T, 4, ALGO>(d, p);
     case 2: return launch<QcJpl4096, T, 1, ALGO>(d, p);
+    case 3: return onchip_launch(d, p);
     default: set_error("no RESIDENT specialisation for this code"); return LDPC_B200_EUNSUPPORTED;
     }
 }
@@ -778,7 +758,7 @@ static int launch_prec(ldpc_b200_decoder *d, ResidentParams &p)
 {
     if (d->algo == LDPC_B200_ALGO_SPA) return launch_kind<float, LDPC_B200_ALGO_SPA>(d, p);
 #if RES_PAIR
-    if (d->precision == LDPC_B200_PREC_FP32 && d->code->resident_kind == 2) return launch_pair<QcJpl4096P4>(d, p);
+    if (d->precision == LDPC_B200_PREC_FP32 && resident_kind_of(d) == 2) return launch_pair<QcJpl4096P4>(d, p);
 #endif
     return d->precision == LDPC_B200_PREC_FP64 ? launch_kind<double, LDPC_B200_ALGO_MINSUM>(d, p)
                                                : launch_kind<float, LDPC_B200_ALGO_MINSUM>(d, p);

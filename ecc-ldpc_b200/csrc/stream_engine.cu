@@ -306,34 +306,10 @@ __device__ __forceinline__ int cn_row(T (*lam_r)[TPB], T (*ne_r)[TPB], int tid, 
             x[k] = (k < d) ? -Num<T>::sub(l, n) : Num<T>::inf();
         }
     }
-    if constexpr (ALGO == LDPC_B200_ALGO_SPA) {
-        // fp32 production form (see spa_fp32.cuh): complements c_j = 1 - tanh(|x_j|/2) (pad: x = +inf -> c = 0, the
-        // identity) combined leave-one-out in the tree; the sign of x_j rides in the sign bit of its complement;
-        // magnitude lg2((2-c)/c) capped at the reference's clamp and signed by one FMNMX.XORSIGN; times ln 2.
-        uint32_t sgn = 0;
-#pragma unroll
-        for (int k = 0; k < MAXD; k++) sgn ^= __float_as_uint((float)x[k]);
-        const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
-        float leaf[MAXD];
-#pragma unroll
-        for (int k = 0; k < MAXD; k++)
-            leaf[k] = __uint_as_float(__float_as_uint(spa_compl((float)x[k])) | (__float_as_uint((float)x[k]) & 0x80000000u));
-        BoxTree<float, 0, MAXD, OpComplAbs> tree;
-        tree.build([&](auto ki) { return leaf[decltype(ki)::value]; });
-        tree.down_root([&](auto ki, float others) {
-            constexpr int k = decltype(ki)::value;
-            const float w = FB<float>::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(leaf[k]) & 0x80000000u)));
-            if (FULL || k < d) ne_r[k][tid] = (T)(w * 0.69314718055994531f);
-        });
-    } else {
-        // Min.hs:79-89: ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]; min' is exact and associative, pad = +inf
-        BoxTree<T, 0, MAXD> tree;
-        tree.build([&](auto ki) { return x[decltype(ki)::value]; });
-        tree.down_root([&](auto ki, T others) {
-            constexpr int k = decltype(ki)::value;
-            if (FULL || k < d) ne_r[k][tid] = Num<T>::mul((T)-0.75, others);
-        });
-    }
+    cn_row_core<T, ALGO, MAXD>(x, [&](auto ki, T v) {
+        constexpr int k = decltype(ki)::value;
+        if (FULL || k < d) ne_r[k][tid] = v;
+    });
     return par;
 }
 

@@ -15,7 +15,7 @@ SO_PATH = os.environ.get("LDPC_B200_SO") or os.path.join(_HERE, "libldpc_b200.so
 
 ALGO_SPA, ALGO_MINSUM, ALGO_SPA_CM = 0, 1, 2
 PREC_FP64, PREC_FP32 = 0, 1
-ENGINE_AUTO, ENGINE_STREAM, ENGINE_RESIDENT = 0, 1, 2
+ENGINE_AUTO, ENGINE_STREAM, ENGINE_RESIDENT, ENGINE_ONCHIP = 0, 1, 2, 3
 ALGO = {"spa": ALGO_SPA, "min": ALGO_MINSUM, "minsum": ALGO_MINSUM, "spa_cm": ALGO_SPA_CM, "cm": ALGO_SPA_CM, 0: 0, 1: 1, 2: 2}
 PREC = {"fp64": PREC_FP64, "fp32": PREC_FP32, 0: 0, 1: 1}
 

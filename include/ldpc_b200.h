@@ -58,10 +58,12 @@ enum {
 };
 enum { LDPC_B200_PREC_FP64 = 0, LDPC_B200_PREC_FP32 = 1 };
 /* STREAM   : any H; messages live in HBM, frame-minor layout, one launch per phase.
- * RESIDENT : quasi-cyclic H with single-weight circulants; the whole frame state stays in
+ * RESIDENT : the compiled specialisations for the quasi-cyclic JPL codes; the whole frame state stays in
  *            registers / shared memory of one CTA for all iterations.
- * AUTO     : RESIDENT when the code and precision allow it, else STREAM. */
-enum { LDPC_B200_ENGINE_AUTO = 0, LDPC_B200_ENGINE_STREAM = 1, LDPC_B200_ENGINE_RESIDENT = 2 };
+ * ONCHIP   : any H whose per-frame state (2N + M*(row class + 1) words) fits shared memory; run-time tables.
+ * AUTO     : RESIDENT when a specialisation exists, else ONCHIP when the code fits, else STREAM.
+ * ldpc_b200_decoder_engine reports the engine a decode will actually run on. */
+enum { LDPC_B200_ENGINE_AUTO = 0, LDPC_B200_ENGINE_STREAM = 1, LDPC_B200_ENGINE_RESIDENT = 2, LDPC_B200_ENGINE_ONCHIP = 3 };
 
 typedef struct ldpc_b200_code ldpc_b200_code_t;
 typedef struct ldpc_b200_decoder ldpc_b200_decoder_t;

@@ -484,3 +484,76 @@ def test_cached_mult_variant(gpu_lib, dcodes, builtin_codes, oracles):
     for f in range(4):
         ob, oflag, oit, ocv = oracles["jpl.1024.4.5"].ecc_decode("spa_cm", 10, 1024, 1280, rx[f])
         assert np.array_equal(out[f], ob) and flags[f] == 1
+
+
+ONCHIP_CASES = [("moon.7.13", False), ("1920.1280.3.303", False), ("jpl.1024.4.5", True)]   # (code, force ENGINE_ONCHIP)
+
+
+def _onchip_decoder(gpu_lib, dcode, algo, prec, max_batch, force):
+    dec = gpu_lib.Decoder(dcode, algo, prec, max_batch=max_batch, engine=gpu_lib.ENGINE_ONCHIP if force else gpu_lib.ENGINE_AUTO)
+    assert dec.engine() == gpu_lib.ENGINE_ONCHIP
+    return dec
+
+
+@pytest.mark.parametrize("code_name,force", ONCHIP_CASES)
+def test_onchip_fp64_bit_exact_vs_oracle(code_name, force, gpu_lib, dcodes, builtin_codes, oracles):
+    """Run-time table on-chip kernel, float64 min-sum: decisions, iteration counts and flags identical to the oracle
+    (general codes run on it by default; the JPL code is forced onto it to cover irregular row degrees 3 / 18)."""
+    code = builtin_codes[code_name]
+    F = 900 if code_name == "moon.7.13" else 200
+    llr = awgn_llrs(code, EBN0[code_name], F, 31337, TX[code_name])
+    dec = _onchip_decoder(gpu_lib, dcodes[code_name], "min", "fp64", 128, force)      # F > max_batch: chunking
+    bits, iters, conv = dec.decode(llr, 20)
+    rb, ri, rc = oracles[code_name].decode_batch("min", 20, llr, variant=0)
+    assert np.array_equal(bits, rb) and np.array_equal(iters, ri) and np.array_equal(conv, rc)
+    # iteration cap 0 and 1; a valid codeword; an all-zero LLR vector
+    for cap in (0, 1):
+        b, it, cv = dec.decode(llr[:16], cap)
+        ob, oi, oc = oracles[code_name].decode_batch("min", cap, llr[:16], variant=0)
+        assert np.array_equal(b, ob) and np.array_equal(it, oi) and np.array_equal(cv, oc)
+    z = np.zeros((3, code.N)); z[1] = -5.0; z[2, ::2] = 1e-3
+    b, it, cv = dec.decode(z, 7)
+    ob, oi, oc = oracles[code_name].decode_batch("min", 7, z, variant=0)
+    assert np.array_equal(b, ob) and np.array_equal(it, oi) and np.array_equal(cv, oc)
+    dec.close()
+
+
+@pytest.mark.parametrize("code_name,force", ONCHIP_CASES)
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_onchip_fp32_equals_stream_fp32(code_name, force, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """float32: the on-chip kernel and the STREAM kernels share the check-row arithmetic (bp_tree.cuh) and the
+    reference's fold order, so they agree bit for bit; both within the 99.9 % bar of the float64 oracle."""
+    code = builtin_codes[code_name]
+    F = 2048 if code_name == "moon.7.13" else 384
+    llr = awgn_llrs(code, EBN0[code_name] + 0.2, F, 777, TX[code_name]).astype(np.float32).astype(np.float64)
+    on = _onchip_decoder(gpu_lib, dcodes[code_name], algo, "fp32", 512, force)
+    st = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=512, engine=gpu_lib.ENGINE_STREAM)
+    b1, i1, c1 = on.decode(llr, 20)
+    b2, i2, c2 = st.decode(llr, 20)
+    assert np.array_equal(b1, b2) and np.array_equal(i1, i2) and np.array_equal(c1, c2)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=1 if algo == "min" else 0)
+    assert (b1 == rb).all(axis=1).mean() >= 0.999
+    on.close(); st.close()
+
+
+@pytest.mark.parametrize("code_name,force", ONCHIP_CASES[:2])
+def test_onchip_device_api_and_simulate(code_name, force, gpu_lib, dcodes, builtin_codes):
+    code = builtin_codes[code_name]
+    K, n_tx, F, ebn0 = code.K, code.N, 1500, EBN0[code_name]
+    dec = _onchip_decoder(gpu_lib, dcodes[code_name], "min", "fp32", 2048, force)
+    c = dec.simulate(20, ebn0, K, n_tx, 11, 123456, F)
+    buf = gpu_lib.DeviceBuffer(F * code.N * 4)
+    dec.generate_llr(buf.ptr, ebn0, K, n_tx, 11, 123456, F)
+    dec.sync()
+    llr = buf.download(np.float32, (F, code.N)).astype(np.float64)
+    gb, gi, gc = dec.decode(llr, 20)
+    assert c["frames"] == F and c["sum_iters"] == int(gi.sum()) and c["unconverged"] == int((gc == 0).sum())
+    assert c["bit_errors"] == int(gb[:, :K].sum()) and c["frame_errors"] == int(gb[:, :K].any(axis=1).sum())
+    # fixed iteration count (early_exit = 0): decisions are those of the iteration at which the frame first converged
+    W = (code.N + 31) // 32
+    bits = gpu_lib.DeviceBuffer(F * W * 4); it = gpu_lib.DeviceBuffer(F * 4); cv = gpu_lib.DeviceBuffer(F)
+    dec.decode_device(buf.ptr, bits.ptr, 20, F, early_exit=False, d_iters=it.ptr, d_conv=cv.ptr)
+    dec.sync()
+    fb = gpu_lib.unpack_bits(bits.download(np.uint32, (F, W)), code.N)
+    assert np.array_equal(fb, gb) and np.array_equal(it.download(np.int32, (F,)), gi)
+    dec.close()
