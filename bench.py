@@ -383,6 +383,10 @@ def main():
             extra["stream_minsum_jpl4096_20it_worst"] = run_cfg(CODE, "min", lib.ENGINE_STREAM, 8192, 20, EBN0_WORST, N_TX)
             extra["stream_spa_jpl4096_20it_worst"] = run_cfg(CODE, "spa", lib.ENGINE_STREAM, 8192, 20, EBN0_WORST, N_TX)
             extra["stream_minsum_1920.1280.3.303_20it_worst"] = run_cfg("1920.1280.3.303", "min", lib.ENGINE_STREAM, 32768, 20, 0.0, 1920)
+            # the run-time table on-chip engine (general codes whose frame state fits shared memory)
+            extra["onchip_minsum_1920.1280.3.303_20it_worst"] = run_cfg("1920.1280.3.303", "min", lib.ENGINE_AUTO, 65536, 20, 0.0, 1920)
+            extra["onchip_minsum_1920.1280.3.303_20it_2.5dB"] = run_cfg("1920.1280.3.303", "min", lib.ENGINE_AUTO, 65536, 20, 2.5, 1920)
+            extra["onchip_spa_moon.7.13_20it_3.0dB"] = run_cfg("moon.7.13", "spa", lib.ENGINE_AUTO, 262144, 20, 3.0, 20)
 
     # ---------------- CPU baseline beside it (rank 0, bounded sample) ----------------
     cpu = None

@@ -10,7 +10,7 @@
 // One frame = TPF threads (32..256): thread t owns checks t, t+TPF, ... in the check phase and variables t, t+TPF, ...
 // in the variable phase.  Reference lines: driver loop Orig.hs:58-71; syndrome Orig.hs:73-78; check update Min.hs:75-89 /
 // Orig.hs:81-92 (fp32 sum-product in the complement-domain tree of bp_tree.cuh); variable update Orig.hs:95-98 with
-// the reference's right-fold association, so the float64 instance is bit-identical to the oracle and the float32
+// the reference's right-fold association, so the float64 instance reproduces the reference arithmetic bit for bit and the float32
 // instance to the STREAM engine.
 #include "common.cuh"
 #include "philox.cuh"
