@@ -263,9 +263,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B * b_alg / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_static = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch_per_frame")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("dram_bytes_per_launch_per_frame")
+        ncu_static = tj.get("ncu")
         if traffic is not None:
             traffic = traffic * B
     except Exception:
@@ -388,6 +390,18 @@ def main():
             extra["onchip_minsum_1920.1280.3.303_20it_2.5dB"] = run_cfg("1920.1280.3.303", "min", lib.ENGINE_AUTO, 65536, 20, 2.5, 1920)
             extra["onchip_spa_moon.7.13_20it_3.0dB"] = run_cfg("moon.7.13", "spa", lib.ENGINE_AUTO, 262144, 20, 3.0, 20)
 
+            # the reference tester's own calling pattern: ECC.decode, ONE frame per call (Utils.hs:68-69), host buffers
+            one_rx = h_rx[:1].clone().pin_memory(); one_out = torch.empty((1, code.K), dtype=torch.uint8).pin_memory()
+            one_fl = torch.empty(1, dtype=torch.uint8).pin_memory()
+            for _ in range(20):
+                lib.check(L.ldpc_b200_ecc_decode(rec.h, 1, one_rx.data_ptr(), N_TX, one_out.data_ptr(), one_fl.data_ptr()))
+            t0 = time.perf_counter()
+            for _ in range(200):
+                lib.check(L.ldpc_b200_ecc_decode(rec.h, 1, one_rx.data_ptr(), N_TX, one_out.data_ptr(), one_fl.data_ptr()))
+            us = (time.perf_counter() - t0) / 200 * 1e6
+            extra["single_frame_call"] = {"api": "ldpc_b200_ecc_decode, n_frames = 1 (all 20 iterations run)", "us_per_call": us,
+                                          "frames_per_s": 1e6 / us, "info_gbit_per_s": code.K / us / 1e3}
+
     # ---------------- CPU baseline beside it (rank 0, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -425,6 +439,10 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel_ms": k_ms, "alg_bytes_per_frame": b_alg,
+                         # the frame state is on chip, so beside the algorithmic figure report what HBM really
+                         # carries (ncu dram bytes / live kernel time) and the resources that do bind (from the committed capture)
+                         "measured_dram_gbs": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+                         "binding_resources_ncu": ncu_static,
                          "note": "algorithmic bytes = reference state model 3E+3N words/frame/iteration (SURVEY.md 8d); peak = MEASURED_PEAKS.json hbm_gbs%s" % ("" if peaks else " (fallback)")},
             "cpu_baseline": cpu,
             "extra": extra,

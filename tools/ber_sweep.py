@@ -63,7 +63,7 @@ def main():
         dec = lib.Decoder(dc, algo, "fp32", max_batch=16384)
         orc = oracle.Oracle(code)
         print("## %s, %s, max %d iterations, R = %d/%d, engine %s\n" % (name, {"min": "min-sum (alpha=3/4)", "spa": "sum-product"}[algo], iters, code.K, tx,
-                                                                     {1: "STREAM", 2: "RESIDENT"}[dec.engine()]))
+                                                                     {1: "STREAM", 2: "RESIDENT", 3: "ONCHIP"}[dec.engine()]))
         print("| Eb/N0 dB | GPU frames | GPU FER [95 %] | GPU BER | GPU avg it | CPU frames | CPU FER [95 %] | CPU BER | CPU avg it | agree |")
         print("|---|---|---|---|---|---|---|---|---|---|")
         for eb in grid:
