@@ -85,38 +85,10 @@ static int upload_graph(ldpc_b200_code *c)
         }
         LDPC_CUDA(cudaMalloc(&g.col_ell, sizeof(int32_t) * t.size()));
         LDPC_CUDA(cudaMemcpy(g.col_ell, t.data(), sizeof(int32_t) * t.size(), cudaMemcpyHostToDevice));
-        if (g.row_ell_d && c->E > 0) {
-            // slot of edge e = (its check) * DP + (its position in the check's row)
-            const int DP = g.row_ell_d + 1;
-            std::vector<int32_t> slot_of_edge(c->E), cs(c->E), ts((size_t)c->N * S, 0);
-            for (int m = 0; m < c->M; m++)
-                for (int e = c->row_ptr[m]; e < c->row_ptr[m + 1]; e++) slot_of_edge[e] = m * DP + (e - c->row_ptr[m]);
-            for (int q = 0; q < c->E; q++) cs[q] = slot_of_edge[c->col_edge[q]];
-            for (int j = 0; j < c->N; j++) {
-                int d = t[(size_t)j * S];
-                ts[(size_t)j * S] = d;
-                for (int k = 0; k < D; k++) ts[(size_t)j * S + 1 + k] = d > 0 ? slot_of_edge[t[(size_t)j * S + 1 + k]] : 0;
-            }
-            LDPC_CUDA(cudaMalloc(&g.col_slot_ell, sizeof(int32_t) * ts.size()));
-            LDPC_CUDA(cudaMemcpy(g.col_slot_ell, ts.data(), sizeof(int32_t) * ts.size(), cudaMemcpyHostToDevice));
-            LDPC_CUDA(cudaMalloc(&g.col_slot, sizeof(int32_t) * cs.size()));
-            LDPC_CUDA(cudaMemcpy(g.col_slot, cs.data(), sizeof(int32_t) * cs.size(), cudaMemcpyHostToDevice));
-            // transposed copies
-            std::vector<int32_t> ra((size_t)(g.row_ell_d + 1) * c->M), ca((size_t)S * c->N);
-            g.row_regular = 1;
-            for (int m = 0; m < c->M; m++) {
-                int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
-                if (d != g.row_ell_d) g.row_regular = 0;
-                ra[m] = d;
-                for (int k = 0; k < g.row_ell_d; k++) ra[(size_t)(1 + k) * c->M + m] = d > 0 ? c->col_idx[b + (k < d ? k : d - 1)] : 0;
-            }
-            for (int j = 0; j < c->N; j++)
-                for (int k = 0; k < S; k++) ca[(size_t)k * c->N + j] = ts[(size_t)j * S + k];
-            LDPC_CUDA(cudaMalloc(&g.row_soa, sizeof(int32_t) * ra.size()));
-            LDPC_CUDA(cudaMemcpy(g.row_soa, ra.data(), sizeof(int32_t) * ra.size(), cudaMemcpyHostToDevice));
-            LDPC_CUDA(cudaMalloc(&g.col_soa, sizeof(int32_t) * ca.size()));
-            LDPC_CUDA(cudaMemcpy(g.col_soa, ca.data(), sizeof(int32_t) * ca.size(), cudaMemcpyHostToDevice));
-        }
+    }
+    if (g.row_ell_d && c->E > 0) {
+        int rc = onchip_build_tables(c);          // shared-memory placement + records of the ONCHIP engine (may decline)
+        if (rc) return rc;
     }
     return 0;
 }
@@ -309,7 +281,7 @@ void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
 {
     if (!c) return;
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
-    cudaFree(c->g.row_ell); cudaFree(c->g.col_ell); cudaFree(c->g.col_slot_ell); cudaFree(c->g.col_slot); cudaFree(c->g.row_soa); cudaFree(c->g.col_soa);
+    cudaFree(c->g.row_ell); cudaFree(c->g.col_ell); cudaFree(c->g.oc_tab); cudaFree(c->g.oc_posvar); cudaFree(c->g.col_slot);
     delete c;
 }
 

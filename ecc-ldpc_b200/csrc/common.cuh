@@ -32,14 +32,16 @@ struct DeviceGraph {
     //                                 reference's right fold), first COL_ELL_D of them, last one repeated}
     int32_t *row_ell = nullptr, *col_ell = nullptr;
     int row_ell_d = 0;
-    // ONCHIP engine: the same per-variable records with message SLOTS (check m, position k -> m * (row_ell_d + 1) + k)
-    // instead of edge ids, and the slot of every edge in CSC order for variables of degree > COL_ELL_D
-    int32_t *col_slot_ell = nullptr, *col_slot = nullptr;
-    // the same records transposed (structure of arrays: entry k of all checks / variables is contiguous), so that the
-    // threads of consecutive checks / variables read one cache line per record entry:
-    //   row_soa [row_ell_d + 1][M] : {degree, columns...};  col_soa [COL_ELL_D + 1][N] : {degree, slots in fold order...}
-    int32_t *row_soa = nullptr, *col_soa = nullptr;
-    int row_regular = 0;          // every check has exactly row_ell_d edges
+    // ONCHIP engine (onchip_engine.cu: onchip_build_tables): 16-bit records in the order they are staged into shared
+    // memory -- rowP[D][M] position of the k-th variable of check m in the (permuted) posterior array, rowS[D][M] slot of
+    // message (m,k), rowDeg[M] (irregular codes only), colT[(CD+1)][N] per variable POSITION {degree, message slots in
+    // the order of the reference's right fold}, varPos[N] position of variable j.  Positions and slots are chosen so
+    // that the shared-memory accesses of a warp fall into distinct banks (see onchip_build_tables).
+    uint16_t *oc_tab = nullptr;
+    int oc_tab_elems = 0, oc_se = 0, oc_cd = 0;      // table length, message slots per frame, staged entries per variable
+    int32_t *oc_posvar = nullptr;                    // [N] variable at position p (tail of variables with degree > oc_cd)
+    int32_t *col_slot = nullptr;                     // [E] message slot of every edge in CSC order (same tail)
+    int row_regular = 0;                             // every check has exactly row_ell_d edges
     static constexpr int COL_ELL_D = 8;
 };
 
@@ -128,6 +130,7 @@ int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float
                       uint64_t *d_counters);
 
 // ---- on-chip engine for arbitrary codes (onchip_engine.cu) ----
+int onchip_build_tables(ldpc_b200_code *c);
 bool onchip_fits(const ldpc_b200_code *c, int precision);
 struct ResidentParams;
 int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p);

@@ -3,15 +3,23 @@
 //
 // The RESIDENT kernels are compiled per quasi-cyclic code (circulant tables as immediates).  This is the run-time
 // table counterpart: same frame life cycle (persistent CTAs, atomic work counter, per-frame early exit, fused Philox
-// generation and error counting for ldpc_b200_simulate), but the graph comes from the fixed-stride records of
-// DeviceGraph (row_soa / col_soa, transposed so that a warp reads one line per record entry), read through L1, and all three state arrays live in shared memory:
-//     lam[N]  posteriors      L[N]  channel LLRs      ne[M][DP]  check->variable messages, DP = row class + 1 (odd, so
-//                                                     that the threads of consecutive checks hit distinct banks)
-// One frame = TPF threads (32..256): thread t owns checks t, t+TPF, ... in the check phase and variables t, t+TPF, ...
-// in the variable phase.  Reference lines: driver loop Orig.hs:58-71; syndrome Orig.hs:73-78; check update Min.hs:75-89 /
-// Orig.hs:81-92 (fp32 sum-product in the complement-domain tree of bp_tree.cuh); variable update Orig.hs:95-98 with
-// the reference's right-fold association, so the float64 instance reproduces the reference arithmetic bit for bit and the float32
-// instance to the STREAM engine.
+// generation and error counting for ldpc_b200_simulate), but the graph comes from 16-bit records staged once per
+// persistent CTA into shared memory, next to the state of every frame of the CTA:
+//     lam[N]  posteriors      L[N]  channel LLRs      ne[SE]  check->variable messages
+// One frame = TPF threads (32..256): thread t owns checks t, t+TPF, ... in the check phase and variable POSITIONS
+// t, t+TPF, ... in the variable phase.  The kernel is bound by shared-memory bandwidth, and with the natural placement
+// a quarter of its wavefronts were bank conflicts of the two gathers (posteriors by the checks, messages by the
+// variables).  onchip_build_tables therefore chooses the placement:
+//   * message slots: every edge lies in one "check group" (32 consecutive checks, edge position k) and one "variable
+//     group" (32 consecutive positions, fold position i); a proper 32-colouring of the edges of that bipartite
+//     multigraph (Koenig: it exists, maximum degree 32) is a bank assignment under which BOTH phases touch every bank
+//     at most once per warp access; slot = bank + 32 * rank;
+//   * variable positions: a permutation inside every block of 32 variables (so the variable phase stays conflict-free
+//     by construction), chosen greedily to spread the variables of every check group over distinct banks.
+// Reference lines: driver loop Orig.hs:58-71; syndrome Orig.hs:73-78; check update Min.hs:75-89 / Orig.hs:81-92 (fp32
+// sum-product in the complement-domain tree of bp_tree.cuh); variable update Orig.hs:95-98 with the reference's
+// right-fold association, so the float64 instance reproduces the reference arithmetic bit for bit and the float32
+// instance equals the STREAM engine.
 #include "common.cuh"
 #include "philox.cuh"
 #include <algorithm>
@@ -23,8 +31,8 @@ namespace ldpc {
 #include "resident_common.cuh"
 
 struct OnchipGeom {
-    int TPF, FPC, DP, CD;     // threads per frame, frames per CTA, message row stride, staged entries per variable record
-    size_t frame_elems;       // 2N + M*DP
+    int TPF, FPC, SE, CD;     // threads per frame, frames per CTA, message slots per frame, staged entries per variable record
+    size_t frame_elems;       // 2N + SE
     size_t table_bytes;       // graph records staged in shared memory (uint16), multiple of 16
 };
 
@@ -33,15 +41,17 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 {
     typedef FB<T> F;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int M = g.M, N = g.N, W = (N + 31) / 32, TPF = geo.TPF, DP = geo.DP, CD = geo.CD;
+    const int M = g.M, N = g.N, W = (N + 31) / 32, TPF = geo.TPF, SE = geo.SE, CD = geo.CD;
     const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF, lane = threadIdx.x & 31;
     const int bar = slot + 1, WPF = TPF / 32, wif = tf >> 5;
-    // graph records, staged once per (persistent) CTA and shared by all its frames: 16-bit, structure of arrays
-    //   rowT[(MAXD+1)][M] = {degree, columns...}      colT[(CD+1)][N] = {degree, message slots in fold order...}
-    uint16_t *rowT = reinterpret_cast<uint16_t *>(smem_raw);
-    uint16_t *colT = rowT + (size_t)(MAXD + 1) * M;
-    for (int i = threadIdx.x; i < (MAXD + 1) * M; i += blockDim.x) rowT[i] = (uint16_t)g.row_soa[i];
-    for (int i = threadIdx.x; i < (CD + 1) * N; i += blockDim.x) colT[i] = (uint16_t)g.col_soa[i];
+    // graph records (see DeviceGraph::oc_tab), staged once per persistent CTA and shared by all its frames
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw);
+    for (int i = threadIdx.x; i < g.oc_tab_elems; i += blockDim.x) tab[i] = g.oc_tab[i];
+    const uint16_t *rowP = tab;                              // [MAXD][M] position of the k-th variable of check m
+    const uint16_t *rowS = rowP + (size_t)MAXD * M;          // [MAXD][M] slot of message (m, k)
+    const uint16_t *rowDeg = rowS + (size_t)MAXD * M;        // [M], irregular codes only
+    const uint16_t *colT = rowDeg + (REG ? 0 : M);           // [(CD+1)][N] per position: degree, slots in fold order
+    const uint16_t *varPos = colT + (size_t)(CD + 1) * N;    // [N] position of variable j
     T *lam = reinterpret_cast<T *>(smem_raw + geo.table_bytes) + (size_t)slot * geo.frame_elems;
     T *L = lam + N;
     T *ne = L + N;
@@ -58,7 +68,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
         // ---- frame in: lam = L (Orig.hs:58), ne = 0 (Orig.hs:64-65) ----
         if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
-            for (int j = tf; j < N; j += TPF) { T v = src[j]; L[j] = v; lam[j] = v; }
+            for (int j = tf; j < N; j += TPF) { T v = src[j]; int q = varPos[j]; L[q] = v; lam[q] = v; }
         } else {
             for (int q4 = tf; q4 < (N + 3) / 4; q4 += TPF) {
                 float nz[4];
@@ -66,11 +76,11 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     int j = 4 * q4 + q;
-                    if (j < N) { T v = (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0; L[j] = v; lam[j] = v; }
+                    if (j < N) { T v = (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0; int pos = varPos[j]; L[pos] = v; lam[pos] = v; }
                 }
             }
         }
-        for (int e = tf; e < M * DP; e += TPF) ne[e] = (T)0;
+        for (int e = tf; e < SE; e += TPF) ne[e] = (T)0;
         bar_sync(bar, TPF);
 
         bool done = false;
@@ -80,13 +90,14 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                 // ---- check phase (+ syndrome of the current posteriors) ----
                 int unsat = 0;
                 for (int m = tf; m < M; m += TPF) {
-                    const int d = REG ? MAXD : rowT[m];                      // REG: every check has exactly MAXD edges
-                    T *row = ne + (size_t)m * DP;
+                    const int d = REG ? MAXD : rowDeg[m];                    // REG: every check has exactly MAXD edges
                     T x[MAXD];
+                    int sl[MAXD];
                     int par = 0;
 #pragma unroll
                     for (int k = 0; k < MAXD; k++) {
-                        const T l = lam[rowT[(1 + k) * M + m]], v = row[k];     // padding repeats the last column; masked
+                        sl[k] = rowS[k * M + m];                             // padding entries repeat the last edge; masked
+                        const T l = lam[rowP[k * M + m]], v = ne[sl[k]];
                         if (REG) {
                             par ^= (l > (T)0);                               // Orig.hs:73-78
                             x[k] = -F::sub(l, v);                            // x_j = -(lam_j - ne[m,j])
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                     if (n < p.max_iters)
                         cn_row_core<T, ALGO, MAXD>(x, [&](auto ki, T v) {
                             constexpr int k = decltype(ki)::value;
-                            if (REG || k < d) row[k] = v;
+                            if (REG || k < d) ne[sl[k]] = v;
                         });
                 }
                 const bool any = bar_or(bar, TPF, unsat != 0);               // also: messages visible to the variable phase
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                 unsigned int errs = 0;
                 for (int w = wif; w < W; w += WPF) {
                     const int j = 32 * w + lane;
-                    unsigned int word = __ballot_sync(0xffffffffu, j < N && src[j] > (T)0);
+                    unsigned int word = __ballot_sync(0xffffffffu, j < N && src[varPos[j < N ? j : 0]] > (T)0);
                     if (lane == 0) {
                         if (p.bits) p.bits[(size_t)f * W + w] = word;
                         int lo = 32 * w;
@@ -134,18 +145,19 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
             }
             if (n == p.max_iters || (done && p.early_exit)) break;
 
-            // ---- variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))) ----
-            for (int j = tf; j < N; j += TPF) {
-                const int d = colT[j];
-                T acc = L[j];
-#pragma unroll
-                for (int i = 0; i < DeviceGraph::COL_ELL_D; i++)
-                    if (i < CD && i < d) acc = F::add(ne[colT[(1 + i) * N + j]], acc);                           // last check first
+            // ---- variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))), by position ----
+            for (int q = tf; q < N; q += TPF) {
+                const int d = colT[q];
+                T acc = L[q];
+                const int dd = d < CD ? d : CD;
+                const uint16_t *cp = colT + N + q;
+#pragma unroll 1
+                for (int i = 0; i < dd; i++, cp += N) acc = F::add(ne[*cp], acc);                                // last check first
                 if (d > CD) {
-                    const int q0 = g.col_ptr[j];
-                    for (int q = q0 + d - 1 - CD; q >= q0; q--) acc = F::add(ne[g.col_slot[q]], acc);
+                    const int q0 = g.col_ptr[g.oc_posvar[q]];
+                    for (int e = q0 + d - 1 - CD; e >= q0; e--) acc = F::add(ne[g.col_slot[e]], acc);
                 }
-                lam[j] = acc;
+                lam[q] = acc;
             }
             bar_sync(bar, TPF);
         }
@@ -164,21 +176,145 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 
 static const size_t ONCHIP_MAX_CTA_BYTES = 113 * 1024;      // tables + one frame: at least two CTAs per SM
 
+// Proper 32-colouring of the edges of a bipartite multigraph with maximum degree <= 32 (left node ga[e], right node
+// gb[e]): the textbook alternating-path algorithm.  colour[e] in [0, 32).
+static bool colour_edges_32(int nA, int nB, const std::vector<int> &ga, const std::vector<int> &gb, std::vector<int> &colour)
+{
+    const int E = (int)ga.size(), C = 32;
+    std::vector<int> atA((size_t)nA * C, -1), atB((size_t)nB * C, -1);
+    colour.assign(E, -1);
+    for (int e = 0; e < E; e++) {
+        const int u = ga[e], v = gb[e];
+        int a = -1, b = -1;
+        for (int c = 0; c < C && a < 0; c++) if (atA[(size_t)u * C + c] < 0) a = c;
+        for (int c = 0; c < C && b < 0; c++) if (atB[(size_t)v * C + c] < 0) b = c;
+        if (a < 0 || b < 0) return false;                    // a group with more than 32 edges
+        if (atB[(size_t)v * C + a] >= 0) {
+            // a is taken at v: flip the a/b alternating path that starts at v (it cannot reach u)
+            std::vector<int> path;
+            int node = v, side = 1, want = a;
+            for (;;) {
+                int pe = side ? atB[(size_t)node * C + want] : atA[(size_t)node * C + want];
+                if (pe < 0) break;
+                path.push_back(pe);
+                node = side ? ga[pe] : gb[pe];
+                side ^= 1;
+                want = (want == a) ? b : a;
+            }
+            for (int pe : path) {                            // clear, then re-enter with swapped colours
+                atA[(size_t)ga[pe] * C + colour[pe]] = -1; atB[(size_t)gb[pe] * C + colour[pe]] = -1;
+            }
+            for (int pe : path) {
+                colour[pe] = (colour[pe] == a) ? b : a;
+                atA[(size_t)ga[pe] * C + colour[pe]] = pe; atB[(size_t)gb[pe] * C + colour[pe]] = pe;
+            }
+        }
+        colour[e] = a;
+        atA[(size_t)u * C + a] = e; atB[(size_t)v * C + a] = e;
+    }
+    return true;
+}
+
+// Builds the 16-bit records and the shared-memory placement (see the header comment and DeviceGraph::oc_tab).
+// Leaves g.oc_tab null (the code then runs on STREAM) when the code is outside the engine's limits.
+int onchip_build_tables(ldpc_b200_code *c)
+{
+    DeviceGraph &g = c->g;
+    const int M = c->M, N = c->N, E = c->E, D = g.row_ell_d;
+    if (!D || M <= 0 || E <= 0 || N > 65535) return 0;
+    const int CD = std::min(c->max_col_deg, (int)DeviceGraph::COL_ELL_D);
+    g.row_regular = 1;
+    for (int m = 0; m < M; m++) if (c->row_ptr[m + 1] - c->row_ptr[m] != D) g.row_regular = 0;
+
+    // fold position of every edge inside its variable: 0 = last check (the innermost term of Orig.hs:96)
+    std::vector<int> fold(E), var_of(E), chk_of(E);
+    for (int m = 0; m < M; m++) for (int e = c->row_ptr[m]; e < c->row_ptr[m + 1]; e++) { chk_of[e] = m; var_of[e] = c->col_idx[e]; }
+    for (int j = 0; j < N; j++) {
+        int q0 = c->col_ptr[j], d = c->col_ptr[j + 1] - q0;
+        for (int i = 0; i < d; i++) fold[c->col_edge[q0 + d - 1 - i]] = i;
+    }
+
+    // ---- variable positions: a permutation inside every block of 32, banks spread over the check groups ----
+    const int nCG = ((M + 31) / 32) * D;                      // check group (m / 32, k)
+    std::vector<uint8_t> used((size_t)nCG * 32, 0);
+    std::vector<int> pos(N, -1), posvar(N, -1);
+    std::vector<std::vector<int>> groups_of(N);
+    for (int e = 0; e < E; e++) groups_of[var_of[e]].push_back((chk_of[e] / 32) * D + (e - c->row_ptr[chk_of[e]]));
+    for (int h = 0; h * 32 < N; h++) {
+        bool taken[32] = {false};
+        const int lim = std::min(32, N - h * 32);             // the last block may be short: banks 0 .. lim-1 only
+        for (int j = h * 32; j < h * 32 + lim; j++) {
+            int best = -1, best_cost = 1 << 30;
+            for (int bnk = 0; bnk < lim; bnk++) {
+                if (taken[bnk]) continue;
+                int cost = 0;
+                for (int gq : groups_of[j]) cost += used[(size_t)gq * 32 + bnk];
+                if (cost < best_cost) { best_cost = cost; best = bnk; }
+            }
+            taken[best] = true;
+            pos[j] = h * 32 + best; posvar[h * 32 + best] = j;
+            for (int gq : groups_of[j]) used[(size_t)gq * 32 + best]++;
+        }
+    }
+
+    // ---- message slots: 32-colouring of (check group) x (variable group by POSITION, fold position) ----
+    const int CF = std::max(c->max_col_deg, 1);
+    const int nVG = ((N + 31) / 32) * CF;
+    std::vector<int> ga(E), gb(E), colour;
+    for (int e = 0; e < E; e++) {
+        ga[e] = (chk_of[e] / 32) * D + (e - c->row_ptr[chk_of[e]]);
+        gb[e] = (pos[var_of[e]] / 32) * CF + fold[e];
+    }
+    if (!colour_edges_32(nCG, nVG, ga, gb, colour)) return 0;
+    std::vector<int> rank(32, 0), slot(E);
+    for (int e = 0; e < E; e++) slot[e] = colour[e] + 32 * rank[colour[e]]++;
+    const int SE = 32 * *std::max_element(rank.begin(), rank.end());
+    if (SE > 65535) return 0;
+
+    // ---- records ----
+    std::vector<uint16_t> tab;
+    tab.reserve((size_t)2 * D * M + M + (size_t)(CD + 1) * N + N);
+    for (int pass = 0; pass < 2; pass++)                      // rowP[D][M], then rowS[D][M]
+        for (int k = 0; k < D; k++)
+            for (int m = 0; m < M; m++) {
+                int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
+                int e = d > 0 ? b + (k < d ? k : d - 1) : -1;
+                tab.push_back((uint16_t)(e < 0 ? 0 : (pass == 0 ? pos[var_of[e]] : slot[e])));
+            }
+    if (!g.row_regular) for (int m = 0; m < M; m++) tab.push_back((uint16_t)(c->row_ptr[m + 1] - c->row_ptr[m]));
+    for (int q = 0; q < N; q++) tab.push_back((uint16_t)(c->col_ptr[posvar[q] + 1] - c->col_ptr[posvar[q]]));        // colT[0][q]
+    for (int i = 0; i < CD; i++)
+        for (int q = 0; q < N; q++) {
+            int j = posvar[q], q0 = c->col_ptr[j], d = c->col_ptr[j + 1] - q0;
+            tab.push_back((uint16_t)(d > 0 ? slot[c->col_edge[q0 + d - 1 - (i < d ? i : d - 1)]] : 0));
+        }
+    for (int j = 0; j < N; j++) tab.push_back((uint16_t)pos[j]);
+    std::vector<int32_t> cs(E);
+    for (int q = 0; q < E; q++) cs[q] = slot[c->col_edge[q]];
+
+    LDPC_CUDA(cudaMalloc(&g.oc_tab, sizeof(uint16_t) * tab.size()));
+    LDPC_CUDA(cudaMemcpy(g.oc_tab, tab.data(), sizeof(uint16_t) * tab.size(), cudaMemcpyHostToDevice));
+    LDPC_CUDA(cudaMalloc(&g.oc_posvar, sizeof(int32_t) * N));
+    LDPC_CUDA(cudaMemcpy(g.oc_posvar, posvar.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+    LDPC_CUDA(cudaMalloc(&g.col_slot, sizeof(int32_t) * E));
+    LDPC_CUDA(cudaMemcpy(g.col_slot, cs.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
+    g.oc_tab_elems = (int)tab.size(); g.oc_se = SE; g.oc_cd = CD;
+    return 0;
+}
+
 static bool onchip_geometry(const ldpc_b200_code *c, size_t es, OnchipGeom *out)
 {
     const DeviceGraph &g = c->g;
-    if (!g.row_ell_d || !g.row_soa || !g.col_soa || c->M <= 0 || c->E <= 0) return false;
+    if (!g.oc_tab) return false;
     OnchipGeom geo;
-    geo.DP = g.row_ell_d + 1;
-    geo.CD = std::min(c->max_col_deg, (int)DeviceGraph::COL_ELL_D);
-    if (c->N > 65535 || (size_t)c->M * geo.DP > 65535) return false;                 // 16-bit records
-    geo.frame_elems = (size_t)2 * c->N + (size_t)c->M * geo.DP;
-    geo.table_bytes = (((size_t)(g.row_ell_d + 1) * c->M + (size_t)(geo.CD + 1) * c->N) * sizeof(uint16_t) + 15) / 16 * 16;
+    geo.SE = g.oc_se; geo.CD = g.oc_cd;
+    geo.frame_elems = (size_t)2 * c->N + (size_t)geo.SE;
+    geo.table_bytes = ((size_t)g.oc_tab_elems * sizeof(uint16_t) + 15) / 16 * 16;
     const size_t frame_bytes = geo.frame_elems * es;
-    if (geo.table_bytes + frame_bytes > ONCHIP_MAX_CTA_BYTES) return false;
+    if (geo.table_bytes + frame_bytes + 64 > ONCHIP_MAX_CTA_BYTES) return false;
     int work = std::max(c->M, c->N);
     geo.TPF = std::min(256, std::max(32, ((work + 5) / 6 + 31) / 32 * 32));
-    geo.FPC = (int)std::min<size_t>(std::min(8, 512 / geo.TPF), (ONCHIP_MAX_CTA_BYTES - geo.table_bytes) / frame_bytes);
+    geo.FPC = (int)std::min<size_t>(std::min(8, 512 / geo.TPF), (ONCHIP_MAX_CTA_BYTES - 64 - geo.table_bytes) / frame_bytes);
     if (geo.FPC < 1) geo.FPC = 1;
     if (out) *out = geo;
     return true;

@@ -46,45 +46,6 @@ namespace ldpc {
 #include "bp_tree.cuh"
 #include "resident_common.cuh"
 
-// Two frames per thread, packed as an fp32 pair in one 64-bit register pair.  sm_100 has packed fp32 arithmetic
-// (FADD2 / FMUL2 / FFMA2 on register pairs), 64-bit shared-memory accesses move both frames' words in one
-// instruction, and the address arithmetic is shared between the two frames, so a pair costs ~7.3 instructions per
-// frame-edge-iteration where the single-frame form costs ~12.5.  Only min' (FMNMX.XORSIGN) has no packed form.
-struct f2 { float lo, hi; };
-__device__ __forceinline__ f2 mk_f2(float lo, float hi) { f2 r; r.lo = lo; r.hi = hi; return r; }
-__device__ __forceinline__ float f2_lo(f2 a) { return a.lo; }
-__device__ __forceinline__ float f2_hi(f2 a) { return a.hi; }
-#ifndef RES_PAIR_PACKED
-#define RES_PAIR_PACKED 0      // 1: FADD2 / FMUL2 (packed fp32x2); 0: scalar arithmetic, only the smem accesses are 64-bit
-#endif
-__device__ __forceinline__ unsigned long long f2_pack(f2 a) { unsigned long long v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a.lo), "f"(a.hi)); return v; }
-__device__ __forceinline__ f2 f2_unpack(unsigned long long v) { f2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.lo), "=f"(r.hi) : "l"(v)); return r; }
-template <> struct FB<f2> {
-    typedef unsigned long long B;
-    static constexpr B SIGN = 0x8000000080000000ull;
-    static __device__ __forceinline__ B bits(f2 x) { return ((B)__float_as_uint(x.hi) << 32) | (B)__float_as_uint(x.lo); }
-#if RES_PAIR_PACKED
-    static __device__ __forceinline__ f2 add(f2 a, f2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r); }
-    static __device__ __forceinline__ f2 sub(f2 a, f2 b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r); }
-    static __device__ __forceinline__ f2 mul(f2 a, f2 b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r); }
-#else
-    static __device__ __forceinline__ f2 add(f2 a, f2 b) { return mk_f2(__fadd_rn(a.lo, b.lo), __fadd_rn(a.hi, b.hi)); }
-    static __device__ __forceinline__ f2 sub(f2 a, f2 b) { return mk_f2(__fsub_rn(a.lo, b.lo), __fsub_rn(a.hi, b.hi)); }
-    static __device__ __forceinline__ f2 mul(f2 a, f2 b) { return mk_f2(__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)); }
-#endif
-    static __device__ __forceinline__ f2 box(f2 a, f2 b) { return mk_f2(FB<float>::box(a.lo, b.lo), FB<float>::box(a.hi, b.hi)); }
-    template <int OFF> static __device__ __forceinline__ f2 lds(uint32_t addr)
-    {
-        f2 v;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.lo), "=f"(v.hi) : "r"(addr), "n"(OFF));
-        return v;
-    }
-    template <int OFF> static __device__ __forceinline__ void sts(uint32_t addr, f2 v)
-    {
-        asm volatile("st.shared.v2.f32 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "f"(v.lo), "f"(v.hi));
-    }
-};
-
 // Compile-time layout of the per-thread message registers: the rows of a part, in order, each with row_deg slots.
 template <class C> struct QcMap {
     static __host__ __device__ constexpr int reg_base(int r)
@@ -128,7 +89,6 @@ __device__ __forceinline__ uint32_t rot(uint32_t P)
 }
 
 template <typename T> __device__ __forceinline__ T minus34() { return (T)-0.75; }
-template <> __device__ __forceinline__ f2 minus34<f2>() { return mk_f2(-0.75f, -0.75f); }
 
 // Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
 // round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
@@ -488,138 +448,6 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
     }
 }
 
-// ---- two frames per CTA thread (packed pair) -----------------------------------------------------------------
-// The CTA decodes frames 2q and 2q+1 together.  smem holds interleaved pairs mu2[N], negL2[N] (8 bytes per variable).
-// Each frame stops on its own (output written when it converges or runs out of iterations); the pair goes on until
-// both have stopped, the extra iterations of the first finisher are discarded.
-template <class C, int H>
-__device__ __forceinline__ void decode_pair(const ResidentParams &p, unsigned int fa, bool have_b, const f2 *mu, const f2 *negL,
-                                            uint32_t P, volatile unsigned int *s_flags, int tf, int lane, FrameCounters &cnt)
-{
-    typedef QcMap<C> Mp;
-    constexpr int N = Mp::N, TPF = C::NP * C::SZ, WPF = TPF / 32, W = N / 32;
-    const int wif = tf >> 5;
-    f2 ne[Mp::NEH];
-#pragma unroll
-    for (int e = 0; e < Mp::NEH; e++) ne[e] = mk_f2(0.0f, 0.0f);
-
-    bool done_a = false, done_b = !have_b;
-    for (int n = 0;; n++) {
-        const bool last = (n == p.max_iters);
-        unsigned long long u = last ? synd_phase<C, f2, H>(P) : cn_phase<C, f2, H, LDPC_B200_ALGO_MINSUM>(ne, P);
-        // vote without a second barrier: unsatisfied threads raise this iteration's flags (benign same-value race)
-        volatile unsigned int *fl = s_flags + 2 * (n & 1);
-        if ((uint32_t)u) fl[0] = 1u;
-        if ((uint32_t)(u >> 32)) fl[1] = 1u;
-        bar_sync(1, TPF);
-        const bool any_a = fl[0] != 0, any_b = fl[1] != 0;
-        if (tf == 0) { s_flags[2 * ((n + 1) & 1)] = 0u; s_flags[2 * ((n + 1) & 1) + 1] = 0u; }   // next iteration's flags
-        const bool fin_a = !done_a && (!any_a || last), fin_b = !done_b && (!any_b || last);
-        if (fin_a || fin_b) {
-#pragma unroll
-            for (int which = 0; which < 2; which++) {
-                const bool fin = which ? fin_b : fin_a;
-                if (!fin) continue;
-                const bool conv = which ? !any_b : !any_a;
-                const unsigned int f = fa + which;
-                const f2 *src = conv ? mu : negL;
-                unsigned int errs = 0;
-                for (int w = wif; w < W; w += WPF) {
-                    f2 v = src[32 * w + lane];
-                    float x = which ? f2_hi(v) : f2_lo(v);
-                    unsigned int word = __ballot_sync(0xffffffffu, x < 0.0f);
-                    if (lane == 0) {
-                        if (p.bits) p.bits[(size_t)f * W + w] = word;
-                        int lo = 32 * w;
-                        if (lo + 32 <= p.k_info) errs += __popc(word);
-                        else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
-                    }
-                }
-                if (tf == 0) {
-                    if (p.iters) p.iters[f] = n;
-                    if (p.conv) p.conv[f] = conv ? 1 : 0;
-                }
-                if (p.counters) {
-                    bool anyerr = bar_or(2, TPF, errs != 0);
-                    cnt.berr += errs;
-                    if (tf == 0) { cnt.frames++; cnt.ferr += anyerr; cnt.iters += n; cnt.unconv += !conv; }
-                }
-            }
-            done_a |= fin_a; done_b |= fin_b;
-            bar_sync(1, TPF);                  // snapshot reads of mu before the next stage-0 writes
-        }
-        if (last || (done_a && done_b && p.early_exit)) break;
-        static_for<C::MAXCD>([&](auto qi) {
-            vn_stage<C, f2, H, decltype(qi)::value>(ne, P);
-            bar_sync(1, TPF);
-        });
-    }
-}
-
-template <class C>
-__global__ void __launch_bounds__(C::NP * C::SZ, 1) k_resident_pair(ResidentParams p)
-{
-    typedef QcMap<C> Mp;
-    constexpr int N = Mp::N, SZ = C::SZ, TPF = C::NP * SZ;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int tf = threadIdx.x, h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31;
-    f2 *mu = reinterpret_cast<f2 *>(smem_raw);
-    f2 *negL = mu + N;
-    unsigned int *s_next = reinterpret_cast<unsigned int *>(negL + N);
-    volatile unsigned int *s_flags = s_next + 4;
-    const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
-    const unsigned int n_pairs = (p.n_frames + 1) / 2;
-
-    FrameCounters cnt;
-    for (;;) {
-        if (tf == 0) { s_next[0] = atomicAdd(p.work, 1u); s_flags[0] = 0u; s_flags[1] = 0u; s_flags[2] = 0u; s_flags[3] = 0u; }
-        bar_sync(1, TPF);
-        const unsigned int q = s_next[0];
-        if (q >= n_pairs) break;
-        const unsigned int fa = 2 * q;
-        const bool have_b = fa + 1 < p.n_frames;
-        if (p.llr) {
-            const float *sa = reinterpret_cast<const float *>(p.llr) + (size_t)fa * N;
-            const float *sb = have_b ? sa + N : sa;
-            for (int j = tf; j < N; j += TPF) {
-                f2 v = mk_f2(__fsub_rn(0.0f, sa[j]), __fsub_rn(0.0f, sb[j]));       // 0 - L: never -0.0
-                negL[j] = v; mu[j] = v;
-            }
-        } else {
-            for (int g = tf; g < N / 4; g += TPF) {
-                float na[4], nb[4];
-                awgn4(p.seed, p.first_frame + fa, (uint32_t)g, na);
-                awgn4(p.seed, p.first_frame + fa + (have_b ? 1 : 0), (uint32_t)g, nb);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int j = 4 * g + k;
-                    float a = (j < p.n_tx) ? awgn_llr(na[k], 0, p.sigma, p.scale) : 0.0f;
-                    float b = (j < p.n_tx) ? awgn_llr(nb[k], 0, p.sigma, p.scale) : 0.0f;
-                    f2 v = mk_f2(__fsub_rn(0.0f, a), __fsub_rn(0.0f, b));
-                    negL[j] = v; mu[j] = v;
-                }
-            }
-        }
-        bar_sync(1, TPF);
-        if constexpr (C::NP == 2) {
-            if (h == 0) decode_pair<C, 0>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-            else decode_pair<C, 1>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-        } else {
-            if (h == 0) decode_pair<C, 0>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-            else if (h == 1) decode_pair<C, 1>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-            else if (h == 2) decode_pair<C, 2>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-            else decode_pair<C, 3>(p, fa, have_b, mu, negL, P, s_flags, tf, lane, cnt);
-        }
-    }
-    if (p.counters) {
-        if (lane == 0 && cnt.berr) atomicAdd(&p.counters[2], cnt.berr);
-        if (tf == 0 && cnt.frames) {
-            atomicAdd(&p.counters[0], cnt.frames); atomicAdd(&p.counters[1], cnt.ferr);
-            atomicAdd(&p.counters[3], cnt.iters); atomicAdd(&p.counters[4], cnt.unconv);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -708,41 +536,6 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
     return 0;
 }
 
-// RES_PAIR: decode two frames per CTA thread (64-bit smem accesses, optionally packed fp32x2 arithmetic; min-sum fp32,
-// jpl.4096.4.5, NP = 4).  Correct (all parity tests pass with it) but SLOWER on B200: 78 message registers plus a
-// doubled tree exceed 128 registers per thread at 512 threads per CTA (spills, register moves): 12.7 - 14.3 Gbit/s
-// against 18.0 for the single-frame kernel.  Kept as a build switch, off by default.
-#ifndef RES_PAIR
-#define RES_PAIR 0
-#endif
-
-template <class C>
-static int launch_pair(ldpc_b200_decoder *d, ResidentParams &p)
-{
-    typedef QcMap<C> Mp;
-    auto kern = k_resident_pair<C>;
-    size_t smem = (size_t)2 * Mp::N * sizeof(f2) + 8 * sizeof(unsigned int);
-    static thread_local int blocks_per_sm = 0;
-    static thread_local int n_sm = 0;
-    if (!blocks_per_sm) {
-        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::NP * C::SZ, smem));
-        LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->code->device));
-        if (blocks_per_sm < 1) { set_error("RESIDENT pair kernel does not fit on this device"); blocks_per_sm = 0; return LDPC_B200_EUNSUPPORTED; }
-    }
-    if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
-    LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), d->stream));
-    p.work = d->res_work;
-    unsigned int pairs = (p.n_frames + 1) / 2;
-    unsigned int grid = std::min<unsigned int>(pairs, (unsigned int)(blocks_per_sm * n_sm));
-    if (grid == 0) return 0;
-    kern<<<grid, C::NP * C::SZ, smem, d->stream>>>(p);
-    d->launches++;
-    LDPC_CUDA(cudaGetLastError());
-    return 0;
-}
-
 template <typename T, int ALGO>
 static int launch_kind(ldpc_b200_decoder *d, ResidentParams &p)
 {
@@ -757,9 +550,6 @@ static int launch_kind(ldpc_b200_decoder *d, ResidentParams &p)
 static int launch_prec(ldpc_b200_decoder *d, ResidentParams &p)
 {
     if (d->algo == LDPC_B200_ALGO_SPA) return launch_kind<float, LDPC_B200_ALGO_SPA>(d, p);
-#if RES_PAIR
-    if (d->precision == LDPC_B200_PREC_FP32 && resident_kind_of(d) == 2) return launch_pair<QcJpl4096P4>(d, p);
-#endif
     return d->precision == LDPC_B200_PREC_FP64 ? launch_kind<double, LDPC_B200_ALGO_MINSUM>(d, p)
                                                : launch_kind<float, LDPC_B200_ALGO_MINSUM>(d, p);
 }
