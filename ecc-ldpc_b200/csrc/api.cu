@@ -526,7 +526,9 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
     int N = d->code->N, W = words_per_frame(N);
     size_t in_es = is_double ? sizeof(double) : sizeof(float);
     int cap = d->pipe[0].frames;
-    int chunk = std::max(256, (n_frames + 3) / 4);
+    static int pipe_div = 0;
+    if (!pipe_div) { const char *e = getenv("LDPC_B200_PIPE_DIV"); pipe_div = e ? std::max(1, atoi(e)) : 16; }   // 16 chunks: the un-overlapped tail (decode + D2H of the last chunk) is small; measured 4: 4.92, 8: 5.12, 16: 5.14, 32: 5.00 Gbit/s
+    int chunk = std::max(256, (n_frames + pipe_div - 1) / pipe_div);
     chunk = std::min(chunk, cap);
     // float64 in, float32 decoder: round on the host, ship half the bytes (large batches only: the pool has a wake-up cost)
     const bool narrow = is_double && d->precision == LDPC_B200_PREC_FP32 && n_frames >= 64 && host_narrow_enabled();
