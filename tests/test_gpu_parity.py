@@ -557,3 +557,29 @@ def test_onchip_device_api_and_simulate(code_name, force, gpu_lib, dcodes, built
     fb = gpu_lib.unpack_bits(bits.download(np.uint32, (F, W)), code.N)
     assert np.array_equal(fb, gb) and np.array_equal(it.download(np.int32, (F,)), gi)
     dec.close()
+
+
+@pytest.mark.parametrize("code_name,F,ebn0", [("jpl.1024.4.5", 16384, 3.6), ("jpl.4096.4.5", 3072, 3.5), ("1920.1280.3.303", 8192, 2.2)])
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_production_engines_large_batch_vs_oracle(code_name, F, ebn0, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """BASELINE.json north_star bar at batch scale (config 2 is 16k frames of jpl.1024.4.5): float32 production engines
+    (RESIDENT / ONCHIP through ENGINE_AUTO) against the float64 CPU restatement on identical LLRs, in the waterfall where
+    frames converge late or not at all -- decisions identical on >= 99.9 % of the frames, FER inside the oracle's
+    95 % interval, iteration counts equal on >= 99 %."""
+    code = builtin_codes[code_name]
+    if algo == "spa":
+        F //= 4
+    llr = awgn_llrs(code, ebn0, F, 20261018, TX[code_name])
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=4096)
+    assert dec.engine() in (gpu_lib.ENGINE_RESIDENT, gpu_lib.ENGINE_ONCHIP)
+    bits, iters, conv = dec.decode(llr, 20)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=1 if algo == "min" else 0)
+    same = (bits == rb).all(axis=1)
+    assert same.mean() >= 0.999, (code_name, algo, same.mean())
+    assert (iters == ri).mean() >= 0.99
+    K = code.K
+    fe_gpu, fe_ref = int(bits[:, :K].any(axis=1).sum()), int(rb[:, :K].any(axis=1).sum())
+    p = fe_ref / F
+    half = 1.96 * np.sqrt(max(p * (1 - p), 1.0 / F) / F) + 1.0 / F
+    assert abs(fe_gpu / F - p) <= half, (fe_gpu, fe_ref, F)
+    dec.close()
