@@ -16,6 +16,7 @@ __device__ __forceinline__ bool bar_or(int id, int nthreads, bool pred)
 
 struct ResidentParams {
     const void *llr;               // [F][N] in T, or nullptr: generate on the fly (simulate)
+    int llr_bulk;                  // llr rows are 16-byte aligned and a multiple of 16 bytes: next frame prefetched by bulk copy
     uint32_t *bits;                // [F][N/32] or nullptr
     int32_t *iters;                // [F] or nullptr
     uint8_t *conv;                 // [F] or nullptr

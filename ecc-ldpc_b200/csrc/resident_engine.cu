@@ -45,6 +45,7 @@ namespace ldpc {
 #include "qc_tables.inc"
 #include "bp_tree.cuh"
 #include "resident_common.cuh"
+#include "tma.cuh"
 
 // Compile-time layout of the per-thread message registers: the rows of a part, in order, each with row_deg slots.
 template <class C> struct QcMap {
@@ -397,20 +398,48 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
     const int bar = slot + 1;
     T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;      // negated posterior, see above
     T *negL = mu + N;                                                    // negated channel LLRs
-    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N);
+    // staging row of the NEXT frame's LLRs (host-supplied frames only): fetched by one bulk copy while this frame decodes
+    T *stage = reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N + (size_t)slot * N;
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 3 * N);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(s_next + ((FPC + 1) & ~1)) + slot;
     const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
+    const bool prefetch = p.llr != nullptr && p.llr_bulk;
+    constexpr uint32_t ROWB = N * sizeof(T);
 
     FrameCounters cnt;
-    for (;;) {
-        if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
+    uint32_t phase = 0;
+    if (prefetch) {
+        if (tf == 0) {
+            mbar_init(mbar, 1);
+            const unsigned int nxt = atomicAdd(p.work, 1u);
+            s_next[slot] = nxt;
+            if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+        }
         bar_sync(bar, TPF);
+    }
+    for (;;) {
+        if (!prefetch) {
+            if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
+            bar_sync(bar, TPF);
+        }
         const unsigned int f = s_next[slot];
         if (f >= p.n_frames) break;
 
         // ---- frame in: negL = 0 - L, mu = negL ----
-        if (p.llr) {
+        if (prefetch) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, stage[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
+            if (tf == 0) {
+                const unsigned int nxt = atomicAdd(p.work, 1u);
+                s_next[slot] = nxt;             // read at the top of the next round, many barriers from here
+                if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+            }
+        } else if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
             for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            bar_sync(bar, TPF);
         } else {
             for (int g = tf; g < N / 4; g += TPF) {
                 float nz[4];
@@ -422,8 +451,8 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
                     negL[j] = v; mu[j] = v;
                 }
             }
+            bar_sync(bar, TPF);
         }
-        bar_sync(bar, TPF);
 
         if constexpr (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4 && RES_SPA_LOOPED) {
             decode_frame<C, T, -1, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt, h);
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, sizeof(T) == 4 ? 2 : 1) k
             else if (h == 2) decode_frame<C, T, 2, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
             else decode_frame<C, T, 3, ALGO>(p, f, mu, negL, P, bar, tf, lane, cnt);
         }
-        // all smem reads of this frame are done before the next frame's loads: the bar_sync after s_next does it
+        // all smem reads of this frame are done before the next frame's values arrive: decode_frame ends behind a barrier
     }
 
     if (p.counters) {
@@ -513,7 +542,7 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
 {
     typedef QcMap<C> Mp;
     auto kern = k_resident<C, T, FPC, ALGO>;
-    size_t smem = (size_t)FPC * 2 * Mp::N * sizeof(T) + FPC * sizeof(unsigned int);
+    size_t smem = (size_t)FPC * 3 * Mp::N * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
     static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
     static thread_local int blocks_per_sm = 0;
     static thread_local int n_sm = 0;
@@ -579,6 +608,10 @@ int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_f
     ResidentParams p = {};
     
     p.llr = src; p.bits = d_bits_packed; p.iters = d_iters; p.conv = d_conv; p.counters = nullptr;
+    {
+        const size_t row = (size_t)N * elem_size(d->precision);
+        p.llr_bulk = ((uintptr_t)src % 16 == 0 && row % 16 == 0) ? 1 : 0;     // cp.async.bulk needs 16-byte aligned rows
+    }
     p.n_frames = (unsigned int)n_frames; p.max_iters = max_iters; p.early_exit = early_exit;
     p.k_info = 0; p.n_tx = N;
     return launch_prec(d, p);

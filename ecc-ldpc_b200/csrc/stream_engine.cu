@@ -21,6 +21,7 @@
 namespace ldpc {
 
 #include "bp_tree.cuh"
+#include "tma.cuh"
 
 #ifndef STREAM_TPB
 #define STREAM_TPB 128
@@ -254,39 +255,6 @@ __global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict
 // at 2.7 TB/s with 56 % long-scoreboard stalls; with bulk copies all bytes of the CTA are in flight at once and no
 // register holds an address or a pending value.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_read()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // One check row of one frame from / to the staged rows in shared memory; returns the syndrome parity of the row.
 // FULL: the row has exactly MAXD edges (no masks); otherwise it is padded to MAXD with the neutral element of the check
 // operator, so both forms use the same predicate-free leave-one-out tree as the RESIDENT engine (~2.6 operations per edge).
