@@ -13,4 +13,6 @@ python tools/stream_probe.py 8192 > $O/plain_stream.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 --csv --log-file $O/launches_stream.csv python tools/stream_probe.py 8192 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_cn_tma -s 3 -c 1 -o $O/prof_stream_cn -f python tools/stream_probe.py 8192 > $O/ncu_full_cn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_vn_tma -s 3 -c 1 -o $O/prof_stream_vn -f python tools/stream_probe.py 8192 > $O/ncu_full_vn.log 2>&1
+python tools/stream_probe.py 65536 1920.1280.3.303 min auto > $O/plain_onchip.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_onchip -s 1 -c 1 -o $O/prof_onchip -f python tools/stream_probe.py 65536 1920.1280.3.303 min auto > $O/ncu_full_onchip.log 2>&1
 ls -la $O
