@@ -39,6 +39,10 @@
 #ifndef RES_SPA_LOOPED
 #define RES_SPA_LOOPED 1
 #endif
+// RES_FOLD: min-sum check phase takes x of the last-link edges from the variable phase (see cn_phase)
+#ifndef RES_FOLD
+#define RES_FOLD 1
+#endif
 
 namespace ldpc {
 
@@ -73,6 +77,19 @@ template <class C> struct QcMap {
     }
     static constexpr int NEH = max_part_edges();
     static constexpr int N = C::BC * C::SZ;
+    // edge (r, k) is the LAST link of its column's chain (the first block row of the column): the thread that finishes
+    // the new posterior of that variable is also the one that reads it for edge (r, k) in the next check phase
+    static __host__ __device__ constexpr bool is_final_edge(int r, int k)
+    {
+        int c = C::row_col[r][k];
+        return C::col_row_desc[c][C::col_deg[c] - 1] == r;
+    }
+    static __host__ __device__ constexpr int local_row(int r)       // index of row r inside its part
+    {
+        int h = C::half_of_row[r];
+        for (int q = 0; q < C::HR; q++) if (C::half_rows[h][q] == r) return q;
+        return -1;
+    }
 };
 
 // Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
@@ -99,8 +116,11 @@ template <typename T> __device__ __forceinline__ T minus34() { return (T)-0.75; 
 
 // Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
 // checks is unsatisfied by hard(lam).
-template <class C, typename T, int H, int ALGO>
-__device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], uint32_t P)
+// FOLD (min-sum instances): for the edges that are the last link of their column's chain, the variable phase (or the
+// frame prologue) has already left x = ne + mu in the message register and the sign of mu in fpar[row], so the check
+// phase neither loads nor adds for them: 44 of the 156 shared-memory loads of an iteration disappear.
+template <class C, typename T, int H, int ALGO, bool FOLD>
+__device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
 {
     typedef FB<T> F;
     constexpr int BLK = C::SZ * sizeof(T);
@@ -110,13 +130,16 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ui
         constexpr int d = C::row_deg[r];
         constexpr int base = QcMap<C>::reg_base(r);
         typename F::B par = 0;
+        if constexpr (FOLD) { par = fpar[decltype(qi)::value]; fpar[decltype(qi)::value] = 0; }
         static_for<d>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
-            T m = F::template lds<c * BLK>(rot<C, T, s>(P));
-            par ^= F::bits(m);
-            ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
+            if constexpr (!(FOLD && QcMap<C>::is_final_edge(r, k))) {
+                T m = F::template lds<c * BLK>(rot<C, T, s>(P));
+                par ^= F::bits(m);
+                ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
+            }
         });
         unsat |= par;
         if constexpr (ALGO == LDPC_B200_ALGO_MINSUM) {
@@ -282,8 +305,8 @@ __device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
 // Variable-node stage Q for part H.  Column c builds mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the
 // exact negation of Orig.hs:95-98, one link per stage from the innermost (last block row) outwards; col_stage
 // says which link runs in which stage.  negL sits N*sizeof(T) bytes after mu.
-template <class C, typename T, int H, int Q>
-__device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t P)
+template <class C, typename T, int H, int Q, bool FOLD>
+__device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
 {
     typedef FB<T> F;
     constexpr int BLK = C::SZ * sizeof(T);
@@ -312,7 +335,13 @@ __device__ __forceinline__ void vn_stage(const T (&ne)[QcMap<C>::NEH], uint32_t 
                 constexpr int k = C::col_k_desc[c][step];
                 constexpr int e = QcMap<C>::reg_base(r) + k;
                 uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                F::template sts<c * BLK>(a, F::sub(acc[c], ne[e]));
+                const T val = F::sub(acc[c], ne[e]);
+                F::template sts<c * BLK>(a, val);
+                if constexpr (FOLD && step == C::col_deg[c] - 1) {
+                    // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
+                    ne[e] = F::add(ne[e], val);                                  // x of the next check phase
+                    fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
+                }
             }
         }
     });
@@ -329,9 +358,28 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
     typedef QcMap<C> Mp;
     constexpr int N = Mp::N, TPF = C::NP * C::SZ, WPF = TPF / 32, W = N / 32;
     const int wif = tf >> 5;
+    constexpr bool FOLD = (H >= 0) && ALGO == LDPC_B200_ALGO_MINSUM && RES_FOLD;
     T ne[Mp::NEH];
+    typename FB<T>::B fpar[C::HR];
 #pragma unroll
     for (int e = 0; e < Mp::NEH; e++) ne[e] = (T)0;               // orig_ne = 0 (Orig.hs:64-65)
+#pragma unroll
+    for (int q = 0; q < C::HR; q++) fpar[q] = 0;
+    if constexpr (FOLD) {
+        // prologue of the fold: x = 0 + mu and the sign of mu for the last-link edges (what the variable phase leaves
+        // behind from the second iteration on)
+        static_for<C::HR>([&](auto qi) {
+            constexpr int r = C::half_rows[H][decltype(qi)::value];
+            static_for<C::row_deg[r]>([&](auto ki) {
+                constexpr int k = decltype(ki)::value;
+                if constexpr (Mp::is_final_edge(r, k)) {
+                    T m = FB<T>::template lds<C::row_col[r][k] * C::SZ * (int)sizeof(T)>(rot<C, T, C::row_shift[r][k]>(P));
+                    ne[Mp::reg_base(r) + k] = m;
+                    fpar[decltype(qi)::value] ^= FB<T>::bits(m);
+                }
+            });
+        });
+    }
 
     bool done = false;
     for (int n = 0;; n++) {
@@ -339,7 +387,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
         if (!(done && n == p.max_iters)) {
             bool unsat;
             if constexpr (H >= 0) {
-                unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO>(ne, P)) != 0;
+                unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO, FOLD>(ne, fpar, P)) != 0;
             } else {
                 typename FB<T>::B u = 0;
                 if (n == p.max_iters) dispatch_index<0, C::NP>(h, [&](auto hi) { u = synd_phase<C, T, decltype(hi)::value>(P); });
@@ -379,8 +427,8 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
 
         // ---- variable phase ----
         static_for<C::MAXCD>([&](auto qi) {
-            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value>(ne, P);
-            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value>(ne, P); });
+            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value, FOLD>(ne, fpar, P);
+            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value, false>(ne, fpar, P); });
             bar_sync(bar, TPF);
         });
     }
