@@ -608,6 +608,12 @@ int ldpc_b200_decode(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const 
 int ldpc_b200_decode_punctured(ldpc_b200_decoder_t *d, int max_iters, int n_frames, const double *rx, int rx_stride, int take,
                                uint8_t *msg_bits, int k_take)
 {
+    if (!d) { set_error("decode_punctured: bad arguments"); return LDPC_B200_EINVAL; }
+    const int N = d->code->N;
+    if (take < 1 || take > N || rx_stride < take || k_take < 1 || k_take > N) {
+        set_error("decode_punctured: need 1 <= take <= N = %d, rx_stride >= take, 1 <= k_take <= N (got take %d, stride %d, k_take %d)", N, take, rx_stride, k_take);
+        return LDPC_B200_EINVAL;
+    }
     return decode_host(d, max_iters, n_frames, rx, true, msg_bits, nullptr, nullptr, nullptr, rx_stride, take, k_take);
 }
 

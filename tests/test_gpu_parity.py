@@ -159,6 +159,11 @@ def test_bad_arguments_fail_loudly(gpu_lib, dcodes):
     dec = gpu_lib.Decoder(dcodes["moon.7.13"], "min", "fp32", max_batch=4)
     with pytest.raises(gpu_lib.LdpcError):
         dec.set_engine(gpu_lib.ENGINE_RESIDENT)    # general (non-QC) code
+    # the one-pass decode closure: take / stride / k_take are validated, nothing is silently clamped
+    rx = np.zeros((2, 20)); out = np.zeros((2, 7), dtype=np.uint8)
+    for stride, take, k_take in ((20, 0, 7), (20, 21, 7), (10, 20, 7), (20, 20, 0), (20, 20, 21)):
+        assert L.ldpc_b200_decode_punctured(dec.h, 5, 2, rx.ctypes.data, stride, take, out.ctypes.data, k_take) == -1
+    assert L.ldpc_b200_decode_punctured(dec.h, 5, 2, rx.ctypes.data, 20, 13, out.ctypes.data, 7) == 0
     dec.close()
 
 
