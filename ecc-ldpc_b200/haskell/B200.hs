@@ -4,12 +4,13 @@
 -- Source only: this image has no GHC, so the module is exercised by review, and the same contract is
 -- proven through the ctypes mirror (ecc-ldpc_b200/ecc.py) in tests/test_gpu_parity.py::test_ecc_record_mirror.
 --
--- It registers four decoders next to the existing ECC.Code.LDPC.* ones, built with the reference's own
+-- It registers five decoders next to the existing ECC.Code.LDPC.* ones, built with the reference's own
 -- 'mkLDPC_CodeIO' (src/ECC/Code/LDPC/Utils.hs:91-108) exactly like GPU/CUDA/Arraylet2.hs:60-61 does:
 --
 --   ldpc/b200-minsum/<matrix>/<max-rounds>[/<num>/<den>]      fp32, normalised min-sum (alpha = 3/4)
 --   ldpc/b200-spa/<matrix>/<max-rounds>[/<num>/<den>]         fp32, sum-product
 --   ldpc/b200-minsum-fp64 , ldpc/b200-spa-fp64                 fp64 verification instances
+--   ldpc/b200-spa-cm-fp64                                      the cached-product variant of Fast/CachedMult.hs (fp64)
 --
 -- main/Main.hs only needs  `import qualified ECC.Code.LDPC.GPU.B200 as B200`  and  `<> B200.code`  in `codes`.
 module ECC.Code.LDPC.GPU.B200 (code) where
@@ -69,9 +70,14 @@ decoder algo prec () h@(Q.QuasiCyclic sz m) = do
     let out = S.unsafeFromForeignPtr0 bits n :: S.Vector Word8
     return $ Just $ U.convert $ S.map (/= 0) out
 
+-- | maxThreadCount = 16: mkLDPC calls `decoder0 h` that many times up front (Utils.hs:53) and hands tester thread t the
+-- decoder (t mod 16) (Utils.hs:69).  A decoder handle owns its stream and staging buffers and is not re-entrant, so one
+-- handle per tester thread is what makes concurrent `decode` calls safe without a lock (the reference's own CUDA
+-- variants pass 1 and share their buffers, GPU/CUDA/Arraylet2.hs:61).
 mk :: String -> CInt -> CInt -> Code
-mk name algo prec = mkLDPC_CodeIO name 1 E.encoder (decoder algo prec)
+mk name algo prec = mkLDPC_CodeIO name 16 E.encoder (decoder algo prec)
                                   (check "init" =<< c_init (-1)) (const c_fini)
 
 code :: Code
 code = mk "b200-minsum" 1 1 <> mk "b200-spa" 0 1 <> mk "b200-minsum-fp64" 1 0 <> mk "b200-spa-fp64" 0 0
+    <> mk "b200-spa-cm-fp64" 2 0
