@@ -588,3 +588,32 @@ def test_production_engines_large_batch_vs_oracle(code_name, F, ebn0, algo, gpu_
     half = 1.96 * np.sqrt(max(p * (1 - p), 1.0 / F) / F) + 1.0 / F
     assert abs(fe_gpu / F - p) <= half, (fe_gpu, fe_ref, F)
     dec.close()
+
+
+def test_concurrent_host_threads_one_decoder_each(gpu_lib, dcodes, builtin_codes, oracles):
+    """The reference's tester calls `decode` from several threads, each with its own decoder (Utils.hs:53,62-69:
+    maxThreadCount decoders, thread t uses t mod maxThreadCount).  Four host threads, one handle each, one frame per
+    call, concurrently (ctypes drops the GIL): every result equals the CPU restatement's."""
+    import threading
+    code = builtin_codes["jpl.1024.4.5"]
+    T, calls = 4, 40
+    llr = awgn_llrs(code, 3.8, T * calls, 99, 1280)
+    rb, ri, rc = oracles["jpl.1024.4.5"].decode_batch("min", 20, llr, variant=1)
+    decs = [gpu_lib.Decoder(dcodes["jpl.1024.4.5"], "min", "fp64", max_batch=1) for _ in range(T)]
+    bad, errs = [], []
+
+    def work(t):
+        try:
+            for c in range(calls):
+                f = t * calls + c
+                b, it, cv = decs[t].decode(llr[f:f + 1], 20)
+                if not (np.array_equal(b[0], rb[f]) and it[0] == ri[f] and cv[0] == rc[f]):
+                    bad.append(f)
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs and not bad, (errs, bad)
+    [d.close() for d in decs]
