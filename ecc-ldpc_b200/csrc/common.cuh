@@ -32,13 +32,10 @@ struct DeviceGraph {
     //                                 reference's right fold), first COL_ELL_D of them, last one repeated}
     int32_t *row_ell = nullptr, *col_ell = nullptr;
     int row_ell_d = 0;
-    // ONCHIP engine (onchip_engine.cu: onchip_build_tables): 16-bit records in the order they are staged into shared
-    // memory -- rowP[D][M] position of the k-th variable of check m in the (permuted) posterior array, rowS[D][M] slot of
-    // message (m,k), rowDeg[M] (irregular codes only), colT[(CD+1)][N] per variable POSITION {degree, message slots in
-    // the order of the reference's right fold}, varPos[N] position of variable j.  Positions and slots are chosen so
-    // that the shared-memory accesses of a warp fall into distinct banks (see onchip_build_tables).
+    // ONCHIP engine: 16-bit records in the order they are staged into shared memory (layout and placement:
+    // onchip_engine.cu, onchip_build_tables)
     uint16_t *oc_tab = nullptr;
-    int oc_tab_elems = 0, oc_se = 0, oc_cd = 0;      // table length, message slots per frame, staged entries per variable
+    int oc_tab_elems = 0, oc_se = 0, oc_cd = 0, oc_cdr = 0;   // table length (u16), message slots per frame, staged messages per variable, entries per variable record (4 / 8)
     int32_t *oc_posvar = nullptr;                    // [N] variable at position p (tail of variables with degree > oc_cd)
     int32_t *col_slot = nullptr;                     // [E] message slot of every edge in CSC order (same tail)
     int row_regular = 0;                             // every check has exactly row_ell_d edges

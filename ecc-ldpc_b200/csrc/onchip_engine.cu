@@ -36,22 +36,26 @@ struct OnchipGeom {
     size_t table_bytes;       // graph records staged in shared memory (uint16), multiple of 16
 };
 
-template <typename T, int ALGO, int MAXD, bool REG>
+template <typename T, int ALGO, int MAXD, bool REG, int CDR>
 __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p, OnchipGeom geo)
 {
     typedef FB<T> F;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int M = g.M, N = g.N, W = (N + 31) / 32, TPF = geo.TPF, SE = geo.SE, CD = geo.CD;
+    const int M = g.M, N = g.N, W = (N + 31) / 32, TPF = geo.TPF, SE = geo.SE;
     const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF, lane = threadIdx.x & 31;
     const int bar = slot + 1, WPF = TPF / 32, wif = tf >> 5;
-    // graph records (see DeviceGraph::oc_tab), staged once per persistent CTA and shared by all its frames
-    uint16_t *tab = reinterpret_cast<uint16_t *>(smem_raw);
-    for (int i = threadIdx.x; i < g.oc_tab_elems; i += blockDim.x) tab[i] = g.oc_tab[i];
-    const uint16_t *rowP = tab;                              // [MAXD][M] position of the k-th variable of check m
-    const uint16_t *rowS = rowP + (size_t)MAXD * M;          // [MAXD][M] slot of message (m, k)
-    const uint16_t *rowDeg = rowS + (size_t)MAXD * M;        // [M], irregular codes only
-    const uint16_t *colT = rowDeg + (REG ? 0 : M);           // [(CD+1)][N] per position: degree, slots in fold order
-    const uint16_t *varPos = colT + (size_t)(CD + 1) * N;    // [N] position of variable j
+    // graph records (see onchip_build_tables), staged once per persistent CTA and shared by all its frames
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.oc_tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+        for (int i = threadIdx.x; i < g.oc_tab_elems / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    constexpr int REC4 = (2 * MAXD + 7) / 8;
+    constexpr int ES = sizeof(T) / 4;                        // offsets are stored for 4-byte elements
+    const uint4 *rowA = reinterpret_cast<const uint4 *>(smem_raw);                              // [REC4][M]
+    const uint16_t *rowDeg = reinterpret_cast<const uint16_t *>(rowA + (size_t)REC4 * M);       // [M], irregular codes only
+    const uint16_t *colA = rowDeg + (REG ? 0 : (M + 7) / 8 * 8);                                // [N][CDR]
+    const uint16_t *varPos = colA + ((size_t)N * CDR + 7) / 8 * 8;                              // [N]
     T *lam = reinterpret_cast<T *>(smem_raw + geo.table_bytes) + (size_t)slot * geo.frame_elems;
     T *L = lam + N;
     T *ne = L + N;
@@ -91,13 +95,19 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                 int unsat = 0;
                 for (int m = tf; m < M; m += TPF) {
                     const int d = REG ? MAXD : rowDeg[m];                    // REG: every check has exactly MAXD edges
+                    uint32_t rec[REC4 * 4];                                  // 2 offsets per word
+#pragma unroll
+                    for (int q = 0; q < REC4; q++) {
+                        const uint4 v = rowA[q * M + m];
+                        rec[4 * q] = v.x; rec[4 * q + 1] = v.y; rec[4 * q + 2] = v.z; rec[4 * q + 3] = v.w;
+                    }
+                    auto off = [&](int idx) -> uint32_t { return ((idx & 1) ? (rec[idx >> 1] >> 16) : (rec[idx >> 1] & 0xffffu)) * ES; };
                     T x[MAXD];
-                    int sl[MAXD];
                     int par = 0;
 #pragma unroll
-                    for (int k = 0; k < MAXD; k++) {
-                        sl[k] = rowS[k * M + m];                             // padding entries repeat the last edge; masked
-                        const T l = lam[rowP[k * M + m]], v = ne[sl[k]];
+                    for (int k = 0; k < MAXD; k++) {                         // padding entries repeat the last edge; masked
+                        const T l = *reinterpret_cast<const T *>(reinterpret_cast<const char *>(lam) + off(k));
+                        const T v = *reinterpret_cast<const T *>(reinterpret_cast<const char *>(ne) + off(MAXD + k));
                         if (REG) {
                             par ^= (l > (T)0);                               // Orig.hs:73-78
                             x[k] = -F::sub(l, v);                            // x_j = -(lam_j - ne[m,j])
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                     if (n < p.max_iters)
                         cn_row_core<T, ALGO, MAXD>(x, [&](auto ki, T v) {
                             constexpr int k = decltype(ki)::value;
-                            if (REG || k < d) ne[sl[k]] = v;
+                            if (REG || k < d) *reinterpret_cast<T *>(reinterpret_cast<char *>(ne) + off(MAXD + k)) = v;
                         });
                 }
                 const bool any = bar_or(bar, TPF, unsat != 0);               // also: messages visible to the variable phase
@@ -147,15 +157,19 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 
             // ---- variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))), by position ----
             for (int q = tf; q < N; q += TPF) {
-                const int d = colT[q];
+                uint32_t rec[CDR / 2];
+                if constexpr (CDR == 4) { const uint2 v = reinterpret_cast<const uint2 *>(colA)[q]; rec[0] = v.x; rec[1] = v.y; }
+                else { const uint4 v = reinterpret_cast<const uint4 *>(colA)[q]; rec[0] = v.x; rec[1] = v.y; rec[2] = v.z; rec[3] = v.w; }
+                const int d = rec[0] & 0xffffu;
                 T acc = L[q];
-                const int dd = d < CD ? d : CD;
-                const uint16_t *cp = colT + N + q;
-#pragma unroll 1
-                for (int i = 0; i < dd; i++, cp += N) acc = F::add(ne[*cp], acc);                                // last check first
-                if (d > CD) {
+#pragma unroll
+                for (int i = 0; i < CDR - 1; i++) {                                                              // last check first
+                    const uint32_t o = (((i + 1) & 1) ? (rec[(i + 1) >> 1] >> 16) : (rec[(i + 1) >> 1] & 0xffffu)) * ES;
+                    if (i < d) acc = F::add(*reinterpret_cast<const T *>(reinterpret_cast<const char *>(ne) + o), acc);
+                }
+                if (d > CDR - 1) {
                     const int q0 = g.col_ptr[g.oc_posvar[q]];
-                    for (int e = q0 + d - 1 - CD; e >= q0; e--) acc = F::add(ne[g.col_slot[e]], acc);
+                    for (int e = q0 + d - CDR; e >= q0; e--) acc = F::add(ne[g.col_slot[e]], acc);
                 }
                 lam[q] = acc;
             }
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 
-static const size_t ONCHIP_MAX_CTA_BYTES = 113 * 1024;      // tables + one frame: at least two CTAs per SM
+static const size_t ONCHIP_MAX_CTA_BYTES = 113 * 1024;      // tables + frames of a CTA when two CTAs share an SM
 
 // Proper 32-colouring of the edges of a bipartite multigraph with maximum degree <= 32 (left node ga[e], right node
 // gb[e]): the textbook alternating-path algorithm.  colour[e] in [0, 32).
@@ -222,9 +236,9 @@ int onchip_build_tables(ldpc_b200_code *c)
     DeviceGraph &g = c->g;
     const int M = c->M, N = c->N, E = c->E, D = g.row_ell_d;
     if (!D || M <= 0 || E <= 0 || N > 65535) return 0;
-    const int CD = std::min(c->max_col_deg, (int)DeviceGraph::COL_ELL_D);
     g.row_regular = 1;
     for (int m = 0; m < M; m++) if (c->row_ptr[m + 1] - c->row_ptr[m] != D) g.row_regular = 0;
+    if (D > 8) g.row_regular = 0;                 // mask-free instances exist for the small row classes only
 
     // fold position of every edge inside its variable: 0 = last check (the innermost term of Orig.hs:96)
     std::vector<int> fold(E), var_of(E), chk_of(E);
@@ -269,26 +283,43 @@ int onchip_build_tables(ldpc_b200_code *c)
     std::vector<int> rank(32, 0), slot(E);
     for (int e = 0; e < E; e++) slot[e] = colour[e] + 32 * rank[colour[e]]++;
     const int SE = 32 * *std::max_element(rank.begin(), rank.end());
-    if (SE > 65535) return 0;
 
-    // ---- records ----
+    // ---- records (16-bit, BYTE offsets for 4-byte elements; float64 doubles them at use) ----
+    //   rowA  [REC4][M] x 8 u16 : the check's record {off(lam) of its D variables, off(ne) of its D messages}, cut
+    //                            into 16-byte pieces stored piece-major (threads of consecutive checks read consecutive
+    //                            16-byte words: conflict-free 128-bit loads)
+    //   rowDeg[M]               : degree (irregular codes only)
+    //   colA  [N] x CDR u16     : per variable POSITION {degree, off(ne) of its first CDR-1 messages in fold order}
+    //   varPos[N]               : position of variable j (frame in / decisions out)
+    if ((size_t)N * 4 > 65535 || (size_t)SE * 4 > 65535) return 0;
+    const int REC4 = (2 * D + 7) / 8;
+    const int CDR = c->max_col_deg <= 3 ? 4 : 8;
+    const int CDs = std::min(c->max_col_deg, CDR - 1);            // staged messages per variable
+    auto pad8 = [](std::vector<uint16_t> &v) { while (v.size() % 8) v.push_back(0); };
     std::vector<uint16_t> tab;
-    tab.reserve((size_t)2 * D * M + M + (size_t)(CD + 1) * N + N);
-    for (int pass = 0; pass < 2; pass++)                      // rowP[D][M], then rowS[D][M]
-        for (int k = 0; k < D; k++)
-            for (int m = 0; m < M; m++) {
-                int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
-                int e = d > 0 ? b + (k < d ? k : d - 1) : -1;
-                tab.push_back((uint16_t)(e < 0 ? 0 : (pass == 0 ? pos[var_of[e]] : slot[e])));
+    for (int piece = 0; piece < REC4; piece++)
+        for (int m = 0; m < M; m++) {
+            int b = c->row_ptr[m], d = c->row_ptr[m + 1] - b;
+            for (int w = 0; w < 8; w++) {
+                int idx = piece * 8 + w;                           // entry of the record: [0, D) positions, [D, 2D) slots
+                uint16_t v = 0;
+                if (idx < 2 * D && d > 0) {
+                    int k = idx % D, e = b + (k < d ? k : d - 1);
+                    v = (uint16_t)(4 * (idx < D ? pos[var_of[e]] : slot[e]));
+                }
+                tab.push_back(v);
             }
-    if (!g.row_regular) for (int m = 0; m < M; m++) tab.push_back((uint16_t)(c->row_ptr[m + 1] - c->row_ptr[m]));
-    for (int q = 0; q < N; q++) tab.push_back((uint16_t)(c->col_ptr[posvar[q] + 1] - c->col_ptr[posvar[q]]));        // colT[0][q]
-    for (int i = 0; i < CD; i++)
-        for (int q = 0; q < N; q++) {
-            int j = posvar[q], q0 = c->col_ptr[j], d = c->col_ptr[j + 1] - q0;
-            tab.push_back((uint16_t)(d > 0 ? slot[c->col_edge[q0 + d - 1 - (i < d ? i : d - 1)]] : 0));
         }
+    if (!g.row_regular) { for (int m = 0; m < M; m++) tab.push_back((uint16_t)(c->row_ptr[m + 1] - c->row_ptr[m])); pad8(tab); }
+    for (int q = 0; q < N; q++) {
+        int j = posvar[q], q0 = c->col_ptr[j], d = c->col_ptr[j + 1] - q0;
+        tab.push_back((uint16_t)d);
+        for (int i = 0; i < CDR - 1; i++) tab.push_back((uint16_t)((d > 0 && i < CDs) ? 4 * slot[c->col_edge[q0 + d - 1 - (i < d ? i : d - 1)]] : 0));
+    }
+    pad8(tab);
     for (int j = 0; j < N; j++) tab.push_back((uint16_t)pos[j]);
+    pad8(tab);
+    const int CD = CDs;
     std::vector<int32_t> cs(E);
     for (int q = 0; q < E; q++) cs[q] = slot[c->col_edge[q]];
 
@@ -298,7 +329,7 @@ int onchip_build_tables(ldpc_b200_code *c)
     LDPC_CUDA(cudaMemcpy(g.oc_posvar, posvar.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice));
     LDPC_CUDA(cudaMalloc(&g.col_slot, sizeof(int32_t) * E));
     LDPC_CUDA(cudaMemcpy(g.col_slot, cs.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
-    g.oc_tab_elems = (int)tab.size(); g.oc_se = SE; g.oc_cd = CD;
+    g.oc_tab_elems = (int)tab.size(); g.oc_se = SE; g.oc_cd = CD; g.oc_cdr = CDR;
     return 0;
 }
 
@@ -311,10 +342,12 @@ static bool onchip_geometry(const ldpc_b200_code *c, size_t es, OnchipGeom *out)
     geo.frame_elems = (size_t)2 * c->N + (size_t)geo.SE;
     geo.table_bytes = ((size_t)g.oc_tab_elems * sizeof(uint16_t) + 15) / 16 * 16;
     const size_t frame_bytes = geo.frame_elems * es;
-    if (geo.table_bytes + frame_bytes + 64 > ONCHIP_MAX_CTA_BYTES) return false;
+    size_t cta_bytes = ONCHIP_MAX_CTA_BYTES;                                   // two CTAs per SM ...
+    if (geo.table_bytes + frame_bytes + 64 > cta_bytes) cta_bytes = 224 * 1024;   // ... or one, for the largest codes
+    if (geo.table_bytes + frame_bytes + 64 > cta_bytes) return false;
     int work = std::max(c->M, c->N);
     geo.TPF = std::min(256, std::max(32, ((work + 5) / 6 + 31) / 32 * 32));
-    geo.FPC = (int)std::min<size_t>(std::min(8, 512 / geo.TPF), (ONCHIP_MAX_CTA_BYTES - 64 - geo.table_bytes) / frame_bytes);
+    geo.FPC = (int)std::min<size_t>(std::min(8, 512 / geo.TPF), (cta_bytes - 64 - geo.table_bytes) / frame_bytes);
     if (geo.FPC < 1) geo.FPC = 1;
     if (out) *out = geo;
     return true;
@@ -322,10 +355,10 @@ static bool onchip_geometry(const ldpc_b200_code *c, size_t es, OnchipGeom *out)
 
 bool onchip_fits(const ldpc_b200_code *c, int precision) { return onchip_geometry(c, elem_size(precision), nullptr); }
 
-template <typename T, int ALGO, int MAXD, bool REG>
+template <typename T, int ALGO, int MAXD, bool REG, int CDR>
 static int onchip_launch_t(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo)
 {
-    auto kern = k_onchip<T, ALGO, MAXD, REG>;
+    auto kern = k_onchip<T, ALGO, MAXD, REG, CDR>;
     const int threads = geo.FPC * geo.TPF;
     const size_t smem = geo.table_bytes + (size_t)geo.FPC * geo.frame_elems * sizeof(T) + geo.FPC * sizeof(unsigned int);
     int blocks_per_sm = 0, n_sm = 0;
@@ -349,12 +382,18 @@ static int onchip_launch_t(ldpc_b200_decoder *d, ResidentParams &p, const Onchip
 template <typename T, int ALGO>
 static int onchip_launch_d(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo)
 {
+    // (regular instances only for the small row classes: a regular code of row degree exactly 18 or 32 takes the masked form)
     const bool reg = d->code->g.row_regular != 0;
+    const bool c4 = d->code->g.oc_cdr == 4;
     switch (d->code->g.row_ell_d) {
-    case 4: return reg ? onchip_launch_t<T, ALGO, 4, true>(d, p, geo) : onchip_launch_t<T, ALGO, 4, false>(d, p, geo);
-    case 8: return reg ? onchip_launch_t<T, ALGO, 8, true>(d, p, geo) : onchip_launch_t<T, ALGO, 8, false>(d, p, geo);
-    case 18: return reg ? onchip_launch_t<T, ALGO, 18, true>(d, p, geo) : onchip_launch_t<T, ALGO, 18, false>(d, p, geo);
-    case 32: return reg ? onchip_launch_t<T, ALGO, 32, true>(d, p, geo) : onchip_launch_t<T, ALGO, 32, false>(d, p, geo);
+    case 4:
+        if (reg) return c4 ? onchip_launch_t<T, ALGO, 4, true, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 4, true, 8>(d, p, geo);
+        return c4 ? onchip_launch_t<T, ALGO, 4, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 4, false, 8>(d, p, geo);
+    case 8:
+        if (reg) return c4 ? onchip_launch_t<T, ALGO, 8, true, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 8, true, 8>(d, p, geo);
+        return c4 ? onchip_launch_t<T, ALGO, 8, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 8, false, 8>(d, p, geo);
+    case 18: return c4 ? onchip_launch_t<T, ALGO, 18, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 18, false, 8>(d, p, geo);
+    case 32: return c4 ? onchip_launch_t<T, ALGO, 32, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 32, false, 8>(d, p, geo);
     default: set_error("ONCHIP engine: check degree above 32"); return LDPC_B200_EUNSUPPORTED;
     }
 }
