@@ -617,3 +617,22 @@ def test_concurrent_host_threads_one_decoder_each(gpu_lib, dcodes, builtin_codes
     [x.join() for x in th]
     assert not errs and not bad, (errs, bad)
     [d.close() for d in decs]
+
+
+def test_simulate_counters_pinned(gpu_lib, builtin_codes):
+    """Regression pin (tests/golden/sim_counters.json, written by tests/golden/make_sim_golden.py on a B200): the error
+    counters of ldpc_b200_simulate for fixed Philox frame ranges.  The float32 kernels follow the reference's operation
+    order with explicit roundings (and the sum-product's MUFU approximations are deterministic on sm_100), so a kernel
+    rewrite that changes ONE decision in millions of frames shows up here.  Parity itself is the oracle tests above."""
+    import json
+    cases = json.load(open(os.path.join(GOLDEN, "sim_counters.json")))
+    assert len(cases) >= 8
+    for cs in cases:
+        code = builtin_codes[cs["code"]]
+        dc = gpu_lib.DeviceCode(code)
+        dec = gpu_lib.Decoder(dc, cs["algo"], "fp32", max_batch=16384)
+        assert dec.engine() == cs["engine"]
+        c = dec.simulate(cs["max_iters"], cs["ebn0_db"], code.K, cs["n_tx"], cs["seed"], cs["first_frame"], cs["n_frames"])
+        got = {k: int(c[k]) for k in cs["counters"]}
+        assert got == cs["counters"], (cs["code"], cs["algo"], got, cs["counters"])
+        dec.close(); dc.close()
