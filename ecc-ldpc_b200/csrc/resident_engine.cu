@@ -13,7 +13,7 @@
 //   * the negated posterior mu = -lam and negL = -L live in SHARED memory.  Circulant (r,k) with shift s connects
 //     check (r,i) to variable (c, (i+s) mod SZ): a warp reads/writes 32 consecutive words -> conflict-free.
 //     Every block column is a SZ*sizeof(T)-aligned block, so the rotated address is formed with one add and one
-//     bit-select (LOP3); shifts are compile-time constants and the 67 shift-0 circulants cost nothing.
+//     bit-select (LOP3); shifts are compile-time constants and the 57 shift-0 circulants cost nothing.
 //   * check phase (Min.hs:75-89): x = ne + mu gathered from smem; syndrome parity = xor of the sign bits of mu
 //     (Orig.hs:73-78); leave-one-out reduction with the reference's min' operator (one FMNMX.XORSIGN each) in a
 //     binary tree; ne' = -3/4 * (reduction of the others), in place.
@@ -23,7 +23,14 @@
 //     one thread; a barrier separates stages; which link of which column runs in which stage is scheduled offline
 //     (tools/gen_qc_tables.py) so that the parts carry equal work in every stage.  Same association as the
 //     reference, so the fp64 instance reproduces the reference bit for bit.
-//   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs).
+//     A stage issues all its loads before its first store (the accesses are ordered volatile asm).
+//   * last-link fold (min-sum): the thread that executes the LAST link of a column's chain finishes the new posterior
+//     of that variable and owns one of its edges, so it keeps x = ne' + mu and the sign of mu for that edge in
+//     registers: 44 of the 156 check-phase loads of an iteration never happen.
+//   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs); host-supplied frames:
+//     the NEXT frame's LLR row is fetched by one bulk copy (cp.async.bulk + mbarrier) while the current one decodes.
+//   * sum-product (float32) runs the same phases in the complement domain, with one shared copy of the degree-18 row
+//     arithmetic (cn_phase_spa_looped) because the fully unrolled body did not fit the instruction cache.
 //
 // fp32 is the production instance; fp64 exists to prove the index logic bit-exactly.
 #include "common.cuh"

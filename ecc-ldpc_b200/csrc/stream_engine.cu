@@ -1,15 +1,17 @@
 // stream_engine.cu -- STREAM engine: flooding BP for ANY parity-check matrix, messages in HBM.
 //
 // This engine states the reference algorithm in its own operation order, so the fp64 instance is the
-// message-level verification mode (ldpc_b200_decode_trace) and the fall-back for codes the RESIDENT
-// engine has no specialisation for.
+// message-level verification mode (ldpc_b200_decode_trace); it is also the home of the cached-product variant
+// (LDPC_B200_ALGO_SPA_CM) and the fall-back for codes too large for the on-chip engines.
 //
-// Layout (frame-minor, so every access is coalesced over the frames of a batch):
+// Layout (frame-minor, so every row of a block of TPB frames is one contiguous segment):
 //   L  [N][Bp]   channel LLRs                 lam [N][Bp]  posteriors
 //   ne [E][Bp]   check->variable messages in reference edge order (row-major, ascending column)
-// One thread = one (check, frame) in the check-node kernel, one (variable, frame) in the variable-node
-// kernel.  Algorithmic traffic per frame and iteration is the reference's state model, 3E + 3N words
-// (SURVEY.md 8d): CN reads E ne + gathers lam, writes E ne; VN reads E ne + N L, writes N lam.
+// One thread = one frame of a (check group, frame block) CTA in the check-node kernel, of a (variable group, frame
+// block) CTA in the variable-node kernel; the rows a CTA touches are staged by 1-D bulk copies (k_cn_tma / k_vn_tma;
+// k_cn / k_vn are the dynamic-loop fall-backs).  Algorithmic traffic per frame and iteration is the reference's state
+// model, 3E + 3N words: CN reads E ne + gathers lam, writes E ne; VN reads E ne + N L, writes N lam --
+// and that is what ncu measures in DRAM.
 //
 // Reference lines restated: driver loop Orig.hs:58-71 / Min.hs:54-67; syndrome Orig.hs:73-78;
 // SPA check update Orig.hs:81-92 with atanh' of Utils.hs:113-117; min-sum check update Min.hs:75-87;
