@@ -294,7 +294,7 @@ def main():
     for _ in range(max(1, args.warmup)):
         step_e2e()
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(5, args.steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
