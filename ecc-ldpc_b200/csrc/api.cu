@@ -141,10 +141,11 @@ static int ensure_staging(ldpc_b200_decoder *d)
 }
 
 static int decode_dispatch(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
-                           bool llr_is_double, uint32_t *d_bits, int32_t *d_iters, uint8_t *d_conv)
+                           bool llr_is_double, uint32_t *d_bits, int32_t *d_iters, uint8_t *d_conv,
+                           int src_stride = 0, int src_take = 0)
 {
     if (pick_engine(d) == LDPC_B200_ENGINE_RESIDENT)
-        return resident_decode(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits, d_iters, d_conv);
+        return resident_decode(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits, d_iters, d_conv, src_stride, src_take);
     return stream_decode(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits, d_iters, d_conv, nullptr, nullptr);
 }
 
@@ -532,6 +533,8 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
     chunk = std::min(chunk, cap);
     // float64 in, float32 decoder: round on the host, ship half the bytes (large batches only: the pool has a wake-up cost)
     const bool narrow = is_double && d->precision == LDPC_B200_PREC_FP32 && n_frames >= 64 && host_narrow_enabled();
+    const bool packed_rows = !narrow && is_double && d->precision == LDPC_B200_PREC_FP32 && in_take > 0 && in_take < N &&
+                             in_stride == in_take && pick_engine(d) == LDPC_B200_ENGINE_RESIDENT;
     double total_ms = 0.0;
     int64_t total_launches = 0;
     auto harvest = [&](ldpc_b200_decoder::PipeSet &s) -> int {
@@ -550,7 +553,13 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         rc = harvest(s);                         // also guarantees the set's buffers are free again
         if (rc) break;
         bool dev_double = is_double;
-        if (narrow) {
+        int pk_stride = 0, pk_take = 0;
+        if (packed_rows) {
+            // contiguous rows of in_take doubles: ONE 1-D copy; the device conversion pass spreads them to rows of N floats
+            // and writes the punctured zeros
+            LDPC_CUDA(cudaMemcpyAsync(s.d_in, (const char *)llr + (size_t)f0 * in_take * in_es, (size_t)F * in_take * in_es, cudaMemcpyHostToDevice, d->copy_stream));
+            pk_stride = pk_take = in_take;
+        } else if (narrow) {
             // chunk k is narrowed while chunk k-1 decodes and its H2D copy runs (the calls below are asynchronous)
             if (!s.h_conv) LDPC_CUDA(cudaHostAlloc((void **)&s.h_conv, (size_t)s.frames * N * sizeof(float), cudaHostAllocDefault));
             const int take = in_take > 0 ? in_take : N;
@@ -571,7 +580,7 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
         LDPC_CUDA(cudaStreamWaitEvent(d->stream, s.h2d_done, 0));
         d->launches = 0;
         LDPC_CUDA(cudaEventRecord(s.t0, d->stream));
-        rc = decode_dispatch(d, max_iters, 1, F, s.d_in, dev_double, s.d_bits, s.d_iters, s.d_conv);
+        rc = decode_dispatch(d, max_iters, 1, F, s.d_in, dev_double, s.d_bits, s.d_iters, s.d_conv, pk_stride, pk_take);
         if (!rc && bits_bytes) rc = unpack_bits(d, F, s.d_bits, s.d_bytes);
         if (rc) break;
         LDPC_CUDA(cudaEventRecord(s.t1, d->stream));

@@ -120,8 +120,11 @@ int stream_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_fra
 int resident_kind_for(const ldpc_b200_code *c);          // 0 if no specialisation matches
 bool resident_supports(const ldpc_b200_decoder *d);
 int resident_kind_of(const ldpc_b200_decoder *d);       // 1 / 2 compiled specialisation, 3 run-time table ONCHIP kernel
+// src_take > 0 (float64 source, float32 decoder only): d_llr holds rows of src_take values at a stride of src_stride
+// doubles; the remaining positions of every frame are punctured (LLR 0)
 int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
-                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv);
+                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv,
+                    int src_stride = 0, int src_take = 0);
 int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float sigma, float llr_scale,
                       int k_info, int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
                       uint64_t *d_counters);

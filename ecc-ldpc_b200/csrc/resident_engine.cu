@@ -585,11 +585,16 @@ bool resident_supports(const ldpc_b200_decoder *d)
     return d->code->resident_kind != 0;
 }
 
+// float64 rows of `take` values at a stride of `stride` -> float rows of N values, zero beyond `take` (the punctured
+// positions, Utils.hs:55)
 template <typename T>
-__global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out, size_t n)
+__global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out, size_t n, int N, int stride, int take)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) out[idx] = (T)in[idx];
+    if (idx >= n) return;
+    const size_t f = idx / (size_t)N;
+    const int j = (int)(idx - f * (size_t)N);
+    out[idx] = j < take ? (T)in[f * (size_t)stride + j] : (T)0;
 }
 
 template <class C, typename T, int FPC, int ALGO>
@@ -639,7 +644,7 @@ static int launch_prec(ldpc_b200_decoder *d, ResidentParams &p)
 }
 
 int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_frames, const void *d_llr,
-                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv)
+                    bool llr_is_double, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_conv, int src_stride, int src_take)
 {
     if (!resident_supports(d)) { set_error("RESIDENT engine does not support this decoder"); return LDPC_B200_EUNSUPPORTED; }
     int N = d->code->N;
@@ -653,11 +658,15 @@ int resident_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_f
             d->res_conv_bytes = need;
         }
         size_t n = (size_t)n_frames * N;
-        k_convert_f64<float><<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>((const double *)d_llr, (float *)d->res_conv_buf, n);
+        const int stride = src_take > 0 ? src_stride : N, take = src_take > 0 ? src_take : N;
+        k_convert_f64<float><<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>((const double *)d_llr, (float *)d->res_conv_buf, n, N, stride, take);
         d->launches++;
         src = d->res_conv_buf;
     } else if (!llr_is_double && d->precision == LDPC_B200_PREC_FP64) {
         set_error("fp64 decoder needs float64 LLRs");
+        return LDPC_B200_EINVAL;
+    } else if (src_take > 0) {
+        set_error("packed source rows need the float64 -> float32 conversion pass");
         return LDPC_B200_EINVAL;
     }
     ResidentParams p = {};
