@@ -283,5 +283,12 @@ def builtin_codes_dir():
     """A `codes/` directory in the reference's formats, generated once from the JSON fixtures."""
     root = os.path.join(_CODES_DIR, "_ref_format")
     if not os.path.isfile(os.path.join(root, "jpl.4096.4.5", "G.q")):
-        write_reference_dir(root)
+        # several ranks may arrive here at once (torchrun): build in a private directory, publish with one rename
+        import shutil
+        tmp = "%s.tmp.%d" % (root, os.getpid())
+        write_reference_dir(tmp)
+        try:
+            os.rename(tmp, root)
+        except OSError:                      # another process published first
+            shutil.rmtree(tmp, ignore_errors=True)
     return root
