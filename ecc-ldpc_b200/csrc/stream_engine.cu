@@ -6,7 +6,7 @@
 //
 // Layout (frame-minor, so every row of a block of TPB frames is one contiguous segment):
 //   L  [N][Bp]   channel LLRs                 lam [N][Bp]  posteriors
-//   ne [E][Bp]   check->variable messages in reference edge order (row-major, ascending column)
+//   ne [Bp/TPB][E][TPB]   check->variable messages, frame-block-major, reference edge order (row-major, ascending column)
 // One thread = one frame of a (check group, frame block) CTA in the check-node kernel, of a (variable group, frame
 // block) CTA in the variable-node kernel; the rows a CTA touches are staged by 1-D bulk copies (k_cn_tma / k_vn_tma;
 // k_cn / k_vn are the dynamic-loop fall-backs).  Algorithmic traffic per frame and iteration is the reference's state
@@ -29,6 +29,14 @@ namespace ldpc {
 #define STREAM_TPB 128
 #endif
 static constexpr int TPB = STREAM_TPB;   // threads per block along the frame axis
+
+// The messages are stored frame-block-major, ne[frame block][E][TPB]: the d message rows of a check for one block of
+// frames are then ONE contiguous chunk (one bulk copy in, one out, instead of d each way; the kernels are bound by the
+// number of bulk operations, not by bytes).  L and lam stay [N][Bp]: their rows are gathered one by one anyway.
+__host__ __device__ __forceinline__ size_t ne_at(int e, int f, int E)
+{
+    return ((size_t)(f / TPB) * (size_t)E + (size_t)e) * TPB + (size_t)(f % TPB);
+}
 
 template <typename T> struct Num;
 template <> struct Num<double> {
@@ -155,20 +163,20 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
         uint32_t sgn = 0;
         float run = 0.0f;                                  // identity: c = 0 <=> tanh = 1
         for (int k = 0; k < d; k++) {
-            float x = -(float)Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            float x = -(float)Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[ne_at(b + k, f, g.E)]);
             sgn ^= __float_as_uint(x);
             c[k] = spa_compl(x);
             pre[k] = run;
             run = fmaf(-run, c[k], run + c[k]);
-            ne[(size_t)(b + k) * Bp + f] = (T)x;           // keep x for the sign of the edge
+            ne[ne_at(b + k, f, g.E)] = (T)x;           // keep x for the sign of the edge
         }
         sgn = ~sgn;
         float suf = 0.0f;
         for (int k = d - 1; k >= 0; k--) {
             float others = fmaf(-pre[k], suf, pre[k] + suf);
-            float x = (float)ne[(size_t)(b + k) * Bp + f];
+            float x = (float)ne[ne_at(b + k, f, g.E)];
             float v = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(x)) & 0x80000000u));
-            ne[(size_t)(b + k) * Bp + f] = (T)v;
+            ne[ne_at(b + k, f, g.E)] = (T)v;
             suf = fmaf(-suf, c[k], suf + c[k]);
         }
     } else if (ALGO == LDPC_B200_ALGO_SPA_CM) {
@@ -177,7 +185,7 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
         if (d <= 0) return;
         T t[MAXD];
         for (int k = 0; k < d; k++) {
-            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[ne_at(b + k, f, g.E)]);
             t[k] = Num<T>::tanh_(-(v / (T)2));
         }
         T wa, wb;                                                       // lit x | x >= 1 = (1, x) | otherwise = (x, 1)
@@ -192,35 +200,35 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
         }
         for (int k = 0; k < d; k++) {                                   // sdiv (a,b) c | a == c = b | otherwise = a * (b / c)
             T q = (wa == t[k]) ? wb : Num<T>::mul(wa, wb / t[k]);
-            ne[(size_t)(b + k) * Bp + f] = (T)-2 * atanh_prime<T>(q);
+            ne[ne_at(b + k, f, g.E)] = (T)-2 * atanh_prime<T>(q);
         }
     } else if (ALGO == LDPC_B200_ALGO_SPA) {
         // Orig.hs:86-91: tanh(-((lam_j - ne[m,j]) / 2)) per edge, leave-one-out LEFT fold of (*) from 1.
         T t[MAXD];
         for (int k = 0; k < d; k++) {
-            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T v = Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[ne_at(b + k, f, g.E)]);
             t[k] = Num<T>::tanh_(-(v / (T)2));
         }
         for (int k = 0; k < d; k++) {
             T p = (T)1;
             for (int q = 0; q < d; q++) if (q != k) p = Num<T>::mul(p, t[q]);
-            ne[(size_t)(b + k) * Bp + f] = (T)-2 * atanh_prime<T>(p);
+            ne[ne_at(b + k, f, g.E)] = (T)-2 * atanh_prime<T>(p);
         }
     } else {
         // Min.hs:79-89 in two-minimum form (Model.hs:326-343): exact, because min and sign products are exact.
         T m1 = Num<T>::inf(), m2 = Num<T>::inf();
         int neg = 0;
         for (int k = 0; k < d; k++) {
-            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[ne_at(b + k, f, g.E)]);
             T a = Num<T>::abs_(x);
             if (a < m1) { m2 = m1; m1 = a; } else if (a < m2) m2 = a;
             neg ^= (x < (T)0);
         }
         for (int k = 0; k < d; k++) {
-            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[(size_t)(b + k) * Bp + f]);
+            T x = -Num<T>::sub(lam[(size_t)g.col_idx[b + k] * Bp + f], ne[ne_at(b + k, f, g.E)]);
             T mag = (Num<T>::abs_(x) == m1) ? m2 : m1;
             T v = (neg ^ (x < (T)0)) ? -mag : mag;
-            ne[(size_t)(b + k) * Bp + f] = Num<T>::mul((T)-0.75, v);
+            ne[ne_at(b + k, f, g.E)] = Num<T>::mul((T)-0.75, v);
         }
     }
 }
@@ -238,12 +246,12 @@ __global__ void k_vn(DeviceGraph g, const T *__restrict__ L, const T *__restrict
     const int q0 = g.col_ptr[j], q1 = g.col_ptr[j + 1];
     if (ARRAYLET) {
         if (q1 == q0) { lam[(size_t)j * Bp + f] = L[(size_t)j * Bp + f]; return; }
-        T acc = ne[(size_t)g.col_edge[q1 - 1] * Bp + f];
-        for (int q = q1 - 2; q >= q0; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
+        T acc = ne[ne_at(g.col_edge[q1 - 1], f, g.E)];
+        for (int q = q1 - 2; q >= q0; q--) acc = Num<T>::add(ne[ne_at(g.col_edge[q], f, g.E)], acc);
         lam[(size_t)j * Bp + f] = Num<T>::add(L[(size_t)j * Bp + f], acc);
     } else {
         T acc = L[(size_t)j * Bp + f];
-        for (int q = q1 - 1; q >= q0; q--) acc = Num<T>::add(ne[(size_t)g.col_edge[q] * Bp + f], acc);
+        for (int q = q1 - 1; q >= q0; q--) acc = Num<T>::add(ne[ne_at(g.col_edge[q], f, g.E)], acc);
         lam[(size_t)j * Bp + f] = acc;
     }
 }
@@ -310,15 +318,15 @@ __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restri
         for (int c = 0; c < nchk; c++) rows += (uint32_t)s_rec[c * S + 1];
         mbar_expect_tx(&bar, 2u * rows * ROW);
     }
-    if (tid < 64) {
-        const int q = tid & 31;
-        for (int i = q; i < nchk * MAXD; i += 32) {
+    if (tid < 32) {
+        for (int i = tid; i < nchk * MAXD; i += 32) {
             const int c = i / MAXD, k = i % MAXD;
-            if (k < s_rec[c * S + 1]) {
-                if (tid < 32) bulk_g2s(lam_s[i], lam + (size_t)s_rec[c * S + 2 + k] * Bp + f0, ROW, &bar);
-                else bulk_g2s(ne_s[i], ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ROW, &bar);
-            }
+            if (k < s_rec[c * S + 1]) bulk_g2s(lam_s[i], lam + (size_t)s_rec[c * S + 2 + k] * Bp + f0, ROW, &bar);
         }
+    } else if (tid < 32 + nchk) {
+        const int c = tid - 32;                                             // the check's message rows: one contiguous chunk
+        if (s_rec[c * S + 1] > 0)
+            bulk_g2s(ne_s[c * MAXD], ne + ((size_t)blockIdx.y * g.E + s_rec[c * S]) * TPB, (uint32_t)s_rec[c * S + 1] * ROW, &bar);
     }
     mbar_wait(&bar, 0);
     int par_any = 0;
@@ -333,13 +341,9 @@ __global__ void __launch_bounds__(TPB) k_cn_tma(DeviceGraph g, const T *__restri
     // Frames of this block that have already stopped get their (never used again) messages overwritten too.
     fence_async_smem();
     __syncthreads();
-    if (tid < 32) {
-        bool any = false;
-        for (int i = tid; i < nchk * MAXD; i += 32) {
-            const int c = i / MAXD, k = i % MAXD;
-            if (k < s_rec[c * S + 1]) { bulk_s2g(ne + (size_t)(s_rec[c * S] + k) * Bp + f0, ne_s[i], ROW); any = true; }
-        }
-        if (any) bulk_commit_wait_read();
+    if (tid < nchk && s_rec[tid * S + 1] > 0) {
+        bulk_s2g(ne + ((size_t)blockIdx.y * g.E + s_rec[tid * S]) * TPB, ne_s[tid * MAXD], (uint32_t)s_rec[tid * S + 1] * ROW);
+        bulk_commit_wait_read();
     }
 }
 
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(TPB) k_vn_tma(DeviceGraph g, const T *__restri
         for (int i = tid; i < nvar * R; i += 64) {
             const int v = i / R, r = i % R;
             if (r == 0) bulk_g2s(rows[i], L + (size_t)(j0 + v) * Bp + f0, ROW, &bar);
-            else if (r - 1 < s_rec[v * S]) bulk_g2s(rows[i], ne + (size_t)s_rec[v * S + r] * Bp + f0, ROW, &bar);
+            else if (r - 1 < s_rec[v * S]) bulk_g2s(rows[i], ne + ((size_t)blockIdx.y * g.E + s_rec[v * S + r]) * TPB, ROW, &bar);
         }
     }
     mbar_wait(&bar, 0);
@@ -551,7 +555,7 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             tmp.resize(need);
             LDPC_CUDA(cudaStreamSynchronize(st));
             if (h_c2v && E > 0) {
-                LDPC_CUDA(cudaMemcpy2D(tmp.data(), sizeof(T), s.ne, (size_t)Bp * sizeof(T), sizeof(T), E, cudaMemcpyDeviceToHost));
+                LDPC_CUDA(cudaMemcpy2D(tmp.data(), sizeof(T), s.ne, (size_t)TPB * sizeof(T), sizeof(T), E, cudaMemcpyDeviceToHost));   // frame 0: block 0, lane 0
                 for (int e = 0; e < E; e++) h_c2v[(size_t)n * E + e] = (double)tmp[e];
             }
             if (h_lam) {
