@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <set>
 #include <thread>
 #include <new>
 
@@ -35,6 +36,14 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return LDPC_B200_ENODEV;
     return LDPC_B200_ECUDA;
 }
+
+// Live handles: ldpc_b200_shutdown (the Code's `finalize`, Utils.hs:91-103) releases whatever the host never destroyed,
+// and the destroy functions ignore a handle that is no longer registered (already released, e.g. by shutdown).
+static std::mutex g_reg_mu;
+static std::set<ldpc_b200_decoder *> g_live_decs;
+static std::set<ldpc_b200_code *> g_live_codes;
+template <class H> static void reg_add(std::set<H *> &s, H *h) { std::lock_guard<std::mutex> lk(g_reg_mu); s.insert(h); }
+template <class H> static bool reg_remove(std::set<H *> &s, H *h) { std::lock_guard<std::mutex> lk(g_reg_mu); return s.erase(h) != 0; }
 
 static int require_init()
 {
@@ -216,7 +225,33 @@ int ldpc_b200_init(int device)
     return 0;
 }
 
-void ldpc_b200_shutdown(void) { g_init = false; }
+void ldpc_b200_shutdown(void)
+{
+    // everything the library still holds on the device goes: the replicas of ldpc_b200_simulate_multi, then every live
+    // decoder (streams, staging, pinned buffers), then every live code (device copies of H)
+    ldpc_b200_simulate_multi_release();
+    for (;;) {
+        ldpc_b200_decoder *d = nullptr;
+        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_decs.empty()) d = *g_live_decs.begin(); }
+        if (!d) break;
+        ldpc_b200_decoder_destroy(d);
+    }
+    for (;;) {
+        ldpc_b200_code *c = nullptr;
+        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_codes.empty()) c = *g_live_codes.begin(); }
+        if (!c) break;
+        ldpc_b200_code_destroy(c);
+    }
+    g_init = false;
+}
+
+int ldpc_b200_live_handles(int *codes, int *decoders)
+{
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    if (codes) *codes = (int)g_live_codes.size();
+    if (decoders) *decoders = (int)g_live_decs.size();
+    return 0;
+}
 
 int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_t *col_idx, ldpc_b200_code_t **out)
 {
@@ -237,7 +272,11 @@ int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_
     c->row_ptr.assign(row_ptr, row_ptr + M + 1);
     c->col_idx.assign(col_idx, col_idx + row_ptr[M]);
     finish_code(c);
-    LDPC_CUDA(cudaGetDevice(&c->device));        // the code lives on the CURRENT device (multi-GPU hosts switch devices)
+    {   // the code lives on the CURRENT device (multi-GPU hosts switch devices)
+        cudaError_t ce = cudaGetDevice(&c->device);
+        if (ce != cudaSuccess) { delete c; return cuda_fail(ce, "cudaGetDevice", __FILE__, __LINE__); }
+    }
+    reg_add(g_live_codes, c);
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }
     if (onchip_fits(c, LDPC_B200_PREC_FP32)) c->resident_kind = 3;      // run-time table on-chip kernel
@@ -269,8 +308,12 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
             c->row_ptr[m + 1] = (int32_t)c->col_idx.size();
         }
     finish_code(c);
-    LDPC_CUDA(cudaGetDevice(&c->device));
+    {
+        cudaError_t ce = cudaGetDevice(&c->device);
+        if (ce != cudaSuccess) { delete c; return cuda_fail(ce, "cudaGetDevice", __FILE__, __LINE__); }
+    }
     c->resident_kind = resident_kind_for(c);
+    reg_add(g_live_codes, c);
     rc = upload_graph(c);
     if (rc) { ldpc_b200_code_destroy(c); return rc; }
     if (!c->resident_kind && onchip_fits(c, LDPC_B200_PREC_FP32)) c->resident_kind = 3;
@@ -280,7 +323,7 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
 
 void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
 {
-    if (!c) return;
+    if (!c || !reg_remove(g_live_codes, c)) return;
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
     cudaFree(c->g.row_ell); cudaFree(c->g.col_ell); cudaFree(c->g.oc_tab); cudaFree(c->g.oc_posvar); cudaFree(c->g.col_slot);
     delete c;
@@ -299,7 +342,7 @@ int ldpc_b200_code_info(const ldpc_b200_code_t *c, int *M, int *N, int *E, int *
 int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precision, int max_batch, ldpc_b200_decoder_t **out)
 {
     if (!code || !out || max_batch <= 0) { set_error("decoder_create: bad arguments"); return LDPC_B200_EINVAL; }
-    if (algo != LDPC_B200_ALGO_SPA && algo != LDPC_B200_ALGO_MINSUM && algo != LDPC_B200_ALGO_SPA_CM) { set_error("decoder_create: unknown algo %d", algo); return LDPC_B200_EINVAL; }
+    if (algo < LDPC_B200_ALGO_SPA || algo > LDPC_B200_ALGO_MINSUM_ARRAYLET) { set_error("decoder_create: unknown algo %d", algo); return LDPC_B200_EINVAL; }
     if (algo == LDPC_B200_ALGO_SPA_CM && precision != LDPC_B200_PREC_FP64) {
         set_error("decoder_create: the cached-product sum-product (CachedMult.hs) is a float64 verification variant; use LDPC_B200_ALGO_SPA for float32");
         return LDPC_B200_EUNSUPPORTED;
@@ -310,11 +353,17 @@ int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precisi
     ldpc_b200_decoder *d = new (std::nothrow) ldpc_b200_decoder();
     if (!d) return LDPC_B200_ENOMEM;
     d->code = code; d->algo = algo; d->precision = precision; d->max_batch = max_batch;
-    LDPC_CUDA(cudaSetDevice(code->device));
-    LDPC_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-    LDPC_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-    LDPC_CUDA(cudaEventCreate(&d->ev0));
-    LDPC_CUDA(cudaEventCreate(&d->ev1));
+    d->device = code->device;
+    reg_add(g_live_decs, d);
+    cudaError_t ce = cudaSetDevice(code->device);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&d->ev1);
+    if (ce != cudaSuccess) {                      // nothing half-built escapes: destroy tolerates the null members
+        ldpc_b200_decoder_destroy(d);
+        return cuda_fail(ce, "decoder_create: stream / event creation", __FILE__, __LINE__);
+    }
     *out = d;
     return 0;
 }
@@ -345,8 +394,9 @@ int ldpc_b200_decoder_engine(const ldpc_b200_decoder_t *d)
 
 void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
 {
-    if (!d) return;
-    cudaStreamSynchronize(d->stream);
+    if (!d || !reg_remove(g_live_decs, d)) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
     stream_free(d);
     cudaFree(d->d_in); cudaFree(d->d_bits); cudaFree(d->d_iters); cudaFree(d->d_conv); cudaFree(d->d_counters);
     cudaFree(d->res_work); cudaFree(d->res_conv_buf);
@@ -359,8 +409,10 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
     }
     if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
     if (d->h_pinned) cudaFreeHost(d->h_pinned);
-    cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
-    cudaStreamDestroy(d->stream); cudaStreamDestroy(d->copy_stream);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     delete d;
 }
 
@@ -414,6 +466,7 @@ public:
     // runs fn(part, nparts) on every worker and returns when all are done
     void run(const std::function<void(int, int)> &fn)
     {
+        std::lock_guard<std::mutex> one_job(run_mu_);      // done_.wait releases mu_: callers are serialised here instead
         std::unique_lock<std::mutex> lk(mu_);
         fn_ = &fn; pending_ = (int)workers_.size(); gen_++;
         cv_.notify_all();
@@ -451,7 +504,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex mu_;
+    std::mutex mu_, run_mu_;
     std::condition_variable cv_, done_;
     const std::function<void(int, int)> *fn_ = nullptr;
     int pending_ = 0;
@@ -527,8 +580,7 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
     int N = d->code->N, W = words_per_frame(N);
     size_t in_es = is_double ? sizeof(double) : sizeof(float);
     int cap = d->pipe[0].frames;
-    static int pipe_div = 0;
-    if (!pipe_div) { const char *e = getenv("LDPC_B200_PIPE_DIV"); pipe_div = e ? std::max(1, atoi(e)) : 16; }   // 16 chunks: the un-overlapped tail (decode + D2H of the last chunk) is small; measured 4: 4.92, 8: 5.12, 16: 5.14, 32: 5.00 Gbit/s
+    static const int pipe_div = [] { const char *e = getenv("LDPC_B200_PIPE_DIV"); return e ? std::max(1, atoi(e)) : 16; }();   // (thread-safe magic static) 16 chunks: the un-overlapped tail (decode + D2H of the last chunk) is small; measured 4: 4.92, 8: 5.12, 16: 5.14, 32: 5.00 Gbit/s
     int chunk = std::max(256, (n_frames + pipe_div - 1) / pipe_div);
     chunk = std::min(chunk, cap);
     // float64 in, float32 decoder: round on the host, ship half the bytes (large batches only: the pool has a wake-up cost)

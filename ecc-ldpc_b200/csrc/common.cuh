@@ -72,6 +72,7 @@ struct StreamBuffers {
 struct ldpc_b200_decoder {
     const ldpc_b200_code *code = nullptr;
     int algo = 1, precision = 1, max_batch = 0, engine = 0;
+    int device = -1;             // = code->device, kept here so that destroy does not depend on the code still being alive
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ldpc::StreamBuffers sb;

@@ -280,12 +280,14 @@ extern "C" int ldpc_b200_ecc_open(const char *codes_root, const char *name, int 
     static const struct { const char *nm; int algo, prec; } decs[] = {
         {"b200-minsum", LDPC_B200_ALGO_MINSUM, LDPC_B200_PREC_FP32}, {"b200-spa", LDPC_B200_ALGO_SPA, LDPC_B200_PREC_FP32},
         {"b200-minsum-fp64", LDPC_B200_ALGO_MINSUM, LDPC_B200_PREC_FP64}, {"b200-spa-fp64", LDPC_B200_ALGO_SPA, LDPC_B200_PREC_FP64},
-        {"b200-spa-cm-fp64", LDPC_B200_ALGO_SPA_CM, LDPC_B200_PREC_FP64}};      // the reference's `arraylet-cm` (Fast/CachedMult.hs:229)
+        {"b200-spa-cm-fp64", LDPC_B200_ALGO_SPA_CM, LDPC_B200_PREC_FP64},       // the reference's `arraylet-cm` (Fast/CachedMult.hs:229)
+        {"b200-arraylet-fp64", LDPC_B200_ALGO_SPA_ARRAYLET, LDPC_B200_PREC_FP64},          // `arraylet` (Fast/Arraylet.hs:135)
+        {"b200-arraylet-min-fp64", LDPC_B200_ALGO_MINSUM_ARRAYLET, LDPC_B200_PREC_FP64}};  // `arraylet-min` (Fast/ArrayletMin.hs:136)
     int di = -1;
     if ((xs.size() == 4 || xs.size() == 6) && xs[0] == "ldpc")
         for (int i = 0; i < (int)(sizeof decs / sizeof decs[0]); i++) if (xs[1] == decs[i].nm) di = i;
     bool ok = di >= 0 && all_digits(xs[3]) && (xs.size() == 4 || (all_digits(xs[4]) && all_digits(xs[5])));
-    if (!ok) { set_error("'%s' does not match ldpc/<b200-minsum|b200-spa|b200-minsum-fp64|b200-spa-fp64|b200-spa-cm-fp64>/<matrix-name>/<max-rounds>[/codeword/message]", name); return LDPC_B200_ENOMATCH; }
+    if (!ok) { set_error("'%s' does not match ldpc/<b200-minsum|b200-spa|b200-minsum-fp64|b200-spa-fp64|b200-spa-cm-fp64|b200-arraylet-fp64|b200-arraylet-min-fp64>/<matrix-name>/<max-rounds>[/codeword/message]", name); return LDPC_B200_ENOMATCH; }
 
     ldpc_b200_ecc *e = new ldpc_b200_ecc();
     e->decoder_name = xs[1]; e->code_name = xs[2]; e->codes_root = codes_root;

@@ -45,9 +45,30 @@ static int load_nccl()
     return 0;
 }
 
+// The cached replicas are keyed by the CONTENT of the source code (dimensions + circulant table or CSR arrays), never
+// by its address: a code destroyed and another one allocated at the same address must not hit a stale cache.
+struct CodeKey {
+    int M = 0, N = 0, sz = 0, brows = 0, bcols = 0;
+    std::vector<int32_t> shifts, row_ptr, col_idx;
+    bool valid = false;
+    bool matches(const ldpc_b200_code *c) const
+    {
+        if (!valid || M != c->M || N != c->N || sz != c->sz || brows != c->brows || bcols != c->bcols) return false;
+        return sz > 0 ? shifts == c->shifts : (row_ptr == c->row_ptr && col_idx == c->col_idx);
+    }
+    void take(const ldpc_b200_code *c)
+    {
+        M = c->M; N = c->N; sz = c->sz; brows = c->brows; bcols = c->bcols;
+        if (sz > 0) { shifts = c->shifts; row_ptr.clear(); col_idx.clear(); }
+        else { row_ptr = c->row_ptr; col_idx = c->col_idx; shifts.clear(); }
+        valid = true;
+    }
+};
+
 struct MultiCtx {
-    const ldpc_b200_code *src = nullptr;
+    CodeKey key;
     int n = 0, algo = 0, precision = 0, max_batch = 0;
+    std::vector<int> devs;
     std::vector<ldpc_b200_code_t *> codes;
     std::vector<ldpc_b200_decoder_t *> decs;
     std::vector<uint64_t *> counters;
@@ -60,7 +81,7 @@ static std::mutex g_mu;
 static void destroy_ctx()
 {
     for (size_t g = 0; g < g_ctx.decs.size(); g++) {
-        cudaSetDevice((int)g);
+        cudaSetDevice(g < g_ctx.devs.size() ? g_ctx.devs[g] : (int)g);
         if (g_ctx.decs[g]) ldpc_b200_decoder_destroy(g_ctx.decs[g]);
         if (g < g_ctx.codes.size() && g_ctx.codes[g]) ldpc_b200_code_destroy(g_ctx.codes[g]);
         if (g < g_ctx.counters.size() && g_ctx.counters[g]) cudaFree(g_ctx.counters[g]);
@@ -71,12 +92,14 @@ static void destroy_ctx()
 
 static int build_ctx(const ldpc_b200_code *code, int n, int algo, int precision, int max_batch)
 {
-    if (g_ctx.src == code && g_ctx.n == n && g_ctx.algo == algo && g_ctx.precision == precision && g_ctx.max_batch == max_batch) return 0;
+    if (g_ctx.key.matches(code) && g_ctx.n == n && g_ctx.algo == algo && g_ctx.precision == precision && g_ctx.max_batch == max_batch) return 0;
     destroy_ctx();
-    g_ctx.src = code; g_ctx.n = n; g_ctx.algo = algo; g_ctx.precision = precision; g_ctx.max_batch = max_batch;
+    g_ctx.key.take(code); g_ctx.n = n; g_ctx.algo = algo; g_ctx.precision = precision; g_ctx.max_batch = max_batch;
     g_ctx.codes.assign(n, nullptr); g_ctx.decs.assign(n, nullptr); g_ctx.counters.assign(n, nullptr); g_ctx.comms.assign(n, nullptr);
+    g_ctx.devs.resize(n);
+    for (int g = 0; g < n; g++) g_ctx.devs[g] = g;
     for (int g = 0; g < n; g++) {
-        LDPC_CUDA(cudaSetDevice(g));
+        LDPC_CUDA(cudaSetDevice(g_ctx.devs[g]));
         int rc;
         if (code->sz > 0) rc = ldpc_b200_code_create_qc(code->sz, code->brows, code->bcols, code->shifts.data(), &g_ctx.codes[g]);
         else rc = ldpc_b200_code_create_csr(code->M, code->N, code->row_ptr.data(), code->col_idx.data(), &g_ctx.codes[g]);
@@ -88,9 +111,7 @@ static int build_ctx(const ldpc_b200_code *code, int n, int algo, int precision,
     if (n > 1) {
         int rc = load_nccl();
         if (rc) return rc;
-        std::vector<int> devs(n);
-        for (int g = 0; g < n; g++) devs[g] = g;
-        ncclResult_t r = g_nccl.CommInitAll(g_ctx.comms.data(), n, devs.data());
+        ncclResult_t r = g_nccl.CommInitAll(g_ctx.comms.data(), n, g_ctx.devs.data());
         if (r != ncclSuccess) { set_error("ncclCommInitAll failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return LDPC_B200_ECUDA; }
     }
     return 0;
@@ -120,7 +141,7 @@ extern "C" int ldpc_b200_simulate_multi(const ldpc_b200_code_t *code, int n_gpus
     auto worker = [&](int g) {
         uint64_t cnt = base + ((uint64_t)g < rem ? 1 : 0);
         uint64_t first = first_frame + (uint64_t)g * base + std::min<uint64_t>((uint64_t)g, rem);
-        cudaSetDevice(g);
+        cudaSetDevice(g_ctx.devs[g]);
         cudaStream_t st = (cudaStream_t)ldpc_b200_decoder_stream(g_ctx.decs[g]);
         cudaMemsetAsync(g_ctx.counters[g], 0, 8 * sizeof(uint64_t), st);
         int r = cnt ? ldpc_b200_simulate_device(g_ctx.decs[g], max_iters, early_exit, ebn0_db, k_info, n_tx, seed, first, cnt, g_ctx.counters[g]) : 0;
@@ -147,7 +168,7 @@ extern "C" int ldpc_b200_simulate_multi(const ldpc_b200_code_t *code, int n_gpus
     }
     double ms = 0.0;
     for (int g = 0; g < n_gpus; g++) {
-        cudaSetDevice(g);
+        cudaSetDevice(g_ctx.devs[g]);
         rc = ldpc_b200_decoder_sync(g_ctx.decs[g]);
         double k = 0; int64_t nl = 0;
         if (!rc) rc = ldpc_b200_decoder_last_timing(g_ctx.decs[g], &k, &nl);
@@ -155,7 +176,7 @@ extern "C" int ldpc_b200_simulate_multi(const ldpc_b200_code_t *code, int n_gpus
         ms = std::max(ms, k);
     }
     uint64_t h[8];
-    cudaSetDevice(0);
+    cudaSetDevice(g_ctx.devs[0]);
     LDPC_CUDA(cudaMemcpy(h, g_ctx.counters[0], sizeof h, cudaMemcpyDeviceToHost));
     cudaSetDevice(prev);
     out->frames += h[0]; out->frame_errors += h[1]; out->bit_errors += h[2]; out->sum_iters += h[3]; out->unconverged += h[4];

@@ -35,6 +35,7 @@
 // fp32 is the production instance; fp64 exists to prove the index logic bit-exactly.
 #include "common.cuh"
 #include "philox.cuh"
+#include <atomic>
 #include <utility>
 
 // RES_PARTS: threads per check position (2 or 4). More parts = fewer message registers per thread = more resident
@@ -579,7 +580,7 @@ int resident_kind_of(const ldpc_b200_decoder *d)
 bool resident_supports(const ldpc_b200_decoder *d)
 {
     // min-sum: fp32 and fp64; sum-product: fp32 only (fp64 sum-product is the STREAM engine's literal form)
-    if (d->algo == LDPC_B200_ALGO_SPA_CM) return false;
+    if (d->algo != LDPC_B200_ALGO_SPA && d->algo != LDPC_B200_ALGO_MINSUM) return false;   // the arraylet-order statements live on STREAM
     if (!(d->algo == LDPC_B200_ALGO_MINSUM || d->precision == LDPC_B200_PREC_FP32)) return false;
     if (resident_kind_of(d) == 3) return onchip_fits(d->code, d->precision);
     return d->code->resident_kind != 0;
@@ -597,6 +598,8 @@ __global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out
     out[idx] = j < take ? (T)in[f * (size_t)stride + j] : (T)0;
 }
 
+static constexpr int MAX_DEVICES = 64;
+
 template <class C, typename T, int FPC, int ALGO>
 static int launch(ldpc_b200_decoder *d, ResidentParams &p)
 {
@@ -604,14 +607,20 @@ static int launch(ldpc_b200_decoder *d, ResidentParams &p)
     auto kern = k_resident<C, T, FPC, ALGO>;
     size_t smem = (size_t)FPC * 3 * Mp::N * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
     static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
-    static thread_local int blocks_per_sm = 0;
-    static thread_local int n_sm = 0;
+    // Function attributes (dynamic shared-memory limit, carve-out) are PER DEVICE, so the "already configured" cache is
+    // keyed by the device of the code, not by the calling thread; concurrent first launches write the same values.
+    static std::atomic<int> cfg_bps[MAX_DEVICES], cfg_sm[MAX_DEVICES];
+    const int dev = d->code->device;
+    if (dev < 0 || dev >= MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return LDPC_B200_EINVAL; }
+    int blocks_per_sm = cfg_bps[dev].load(std::memory_order_acquire), n_sm = cfg_sm[dev].load(std::memory_order_relaxed);
     if (!blocks_per_sm) {
         LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FPC * C::NP * C::SZ, smem));
-        LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->code->device));
-        if (blocks_per_sm < 1) { set_error("RESIDENT kernel does not fit on this device"); blocks_per_sm = 0; return LDPC_B200_EUNSUPPORTED; }
+        LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (blocks_per_sm < 1) { set_error("RESIDENT kernel does not fit on this device"); return LDPC_B200_EUNSUPPORTED; }
+        cfg_sm[dev].store(n_sm, std::memory_order_relaxed);
+        cfg_bps[dev].store(blocks_per_sm, std::memory_order_release);
     }
     if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
     LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), d->stream));

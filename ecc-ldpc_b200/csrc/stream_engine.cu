@@ -405,10 +405,20 @@ __global__ void k_finish(const uint8_t *__restrict__ state, const int32_t *__res
     if (out_conv) out_conv[f] = state[f] == 1;
 }
 
+static int stream_alloc_buffers(ldpc_b200_decoder *d);
+
 int stream_alloc(ldpc_b200_decoder *d)
 {
+    if (d->sb.active) return 0;            // `active` is the LAST buffer allocated: set only when all of them exist
+    stream_free(d);
+    int rc = stream_alloc_buffers(d);
+    if (rc) stream_free(d);                // a partial allocation never survives a failed call
+    return rc;
+}
+
+static int stream_alloc_buffers(ldpc_b200_decoder *d)
+{
     StreamBuffers &s = d->sb;
-    if (s.L) return 0;
     const ldpc_b200_code *c = d->code;
     int Bp = ((d->max_batch + TPB - 1) / TPB) * TPB;
     // Row stride of the frame-minor arrays.  All CTAs in flight work on the same block of frames, i.e. on the same offset
@@ -482,7 +492,7 @@ static int launch_vn(ldpc_b200_decoder *d, int fb, int F, int skip_done)
 {
     const DeviceGraph &g = d->code->g;
     StreamBuffers &s = d->sb;
-    if (d->algo == LDPC_B200_ALGO_SPA_CM) {
+    if (d->algo >= LDPC_B200_ALGO_SPA_CM) {        // arraylet association: SPA_CM, SPA_ARRAYLET, MINSUM_ARRAYLET
         k_vn<T, true><<<dim3(g.N, fb), TPB, 0, d->stream>>>(g, (const T *)s.L, (const T *)s.ne, (T *)s.lam, s.state, F, s.Bp, skip_done);
     } else if (g.max_col_deg <= DeviceGraph::COL_ELL_D) {
         constexpr int VPC = 4;
@@ -533,9 +543,12 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
             if (M > 0) { k_syndrome<T><<<gcn, TPB, 0, st>>>(g, (const T *)s.lam, s.state, s.unsat, F, Bp, 1); d->launches++; }
         } else if (M > 0) {
             // converged frames are skipped via `state` when early exit is on; with early_exit = 0 they keep iterating
-            int rc = d->algo == LDPC_B200_ALGO_SPA      ? launch_cn<T, LDPC_B200_ALGO_SPA>(d, fb, F, skip)
-                     : d->algo == LDPC_B200_ALGO_SPA_CM ? launch_cn<T, LDPC_B200_ALGO_SPA_CM>(d, fb, F, skip)
-                                                        : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
+            // (the arraylet statements share the check updates of Arraylet.hs:176-183 = Orig.hs:81-92 and
+            // ArrayletMin.hs:182-189 = Min.hs:75-89; only the posterior association differs, see launch_vn)
+            const int a = d->algo;
+            int rc = (a == LDPC_B200_ALGO_SPA || a == LDPC_B200_ALGO_SPA_ARRAYLET) ? launch_cn<T, LDPC_B200_ALGO_SPA>(d, fb, F, skip)
+                     : a == LDPC_B200_ALGO_SPA_CM                                  ? launch_cn<T, LDPC_B200_ALGO_SPA_CM>(d, fb, F, skip)
+                                                                                   : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
             if (rc) return rc;
         }
         LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));
@@ -576,7 +589,7 @@ int stream_decode(ldpc_b200_decoder *d, int max_iters, int early_exit, int n_fra
 {
     int rc = stream_alloc(d);
     if (rc) return rc;
-    if (n_frames > d->sb.Bp) { set_error("n_frames %d exceeds decoder max_batch", n_frames); return LDPC_B200_EINVAL; }
+    if (n_frames > d->max_batch) { set_error("n_frames %d exceeds decoder max_batch %d", n_frames, d->max_batch); return LDPC_B200_EINVAL; }
     if (d->precision == LDPC_B200_PREC_FP64)
         return stream_decode_t<double>(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits_packed, d_iters, d_conv, h_trace_c2v, h_trace_lam);
     return stream_decode_t<float>(d, max_iters, early_exit, n_frames, d_llr, llr_is_double, d_bits_packed, d_iters, d_conv, h_trace_c2v, h_trace_lam);

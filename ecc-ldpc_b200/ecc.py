@@ -15,7 +15,8 @@ from typing import List, Optional
 from . import codes as _codes
 from . import lib as _lib
 
-DECODERS = ("b200-minsum", "b200-spa", "b200-minsum-fp64", "b200-spa-fp64", "b200-spa-cm-fp64")
+DECODERS = ("b200-minsum", "b200-spa", "b200-minsum-fp64", "b200-spa-fp64", "b200-spa-cm-fp64", "b200-arraylet-fp64",
+            "b200-arraylet-min-fp64")
 USAGE = ["ldpc/%s/<matrix-name>/<max-rounds>[/codeword/message]" % n for n in DECODERS]
 
 

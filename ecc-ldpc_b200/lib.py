@@ -13,14 +13,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("LDPC_B200_SO") or os.path.join(_HERE, "libldpc_b200.so")   # env override: kernel-variant experiments
 
-ALGO_SPA, ALGO_MINSUM, ALGO_SPA_CM = 0, 1, 2
+ALGO_SPA, ALGO_MINSUM, ALGO_SPA_CM, ALGO_SPA_ARRAYLET, ALGO_MINSUM_ARRAYLET = 0, 1, 2, 3, 4
 PREC_FP64, PREC_FP32 = 0, 1
 ENGINE_AUTO, ENGINE_STREAM, ENGINE_RESIDENT, ENGINE_ONCHIP = 0, 1, 2, 3
-ALGO = {"spa": ALGO_SPA, "min": ALGO_MINSUM, "minsum": ALGO_MINSUM, "spa_cm": ALGO_SPA_CM, "cm": ALGO_SPA_CM, 0: 0, 1: 1, 2: 2}
+ALGO = {"spa": ALGO_SPA, "min": ALGO_MINSUM, "minsum": ALGO_MINSUM, "spa_cm": ALGO_SPA_CM, "cm": ALGO_SPA_CM,
+        "arraylet": ALGO_SPA_ARRAYLET, "arraylet-min": ALGO_MINSUM_ARRAYLET, 0: 0, 1: 1, 2: 2, 3: 3, 4: 4}
 PREC = {"fp64": PREC_FP64, "fp32": PREC_FP32, 0: 0, 1: 1}
 
 EXPORTS = [
-    "ldpc_b200_abi_version", "ldpc_b200_last_error", "ldpc_b200_init", "ldpc_b200_shutdown",
+    "ldpc_b200_abi_version", "ldpc_b200_last_error", "ldpc_b200_init", "ldpc_b200_shutdown", "ldpc_b200_live_handles",
     "ldpc_b200_device_count", "ldpc_b200_code_create_csr", "ldpc_b200_code_create_qc",
     "ldpc_b200_code_destroy", "ldpc_b200_code_info", "ldpc_b200_decoder_create",
     "ldpc_b200_decoder_set_engine", "ldpc_b200_decoder_engine", "ldpc_b200_decoder_destroy",
@@ -71,6 +72,8 @@ def load():
     L = C.CDLL(SO_PATH)
     vp, i32, u64, f64 = C.c_void_p, C.c_int, C.c_uint64, C.c_double
     L.ldpc_b200_last_error.restype = C.c_char_p
+    L.ldpc_b200_shutdown.restype = None
+    L.ldpc_b200_live_handles.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.ldpc_b200_code_create_csr.argtypes = [i32, i32, vp, vp, C.POINTER(vp)]
     L.ldpc_b200_code_create_qc.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
     L.ldpc_b200_code_destroy.argtypes = [vp]

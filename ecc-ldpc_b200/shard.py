@@ -33,8 +33,9 @@ def simulate_sharded(dec, max_iters, ebn0_db, k_info, n_tx, seed, first_frame, n
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     first, count = frame_range(rank, world, first_frame, n_frames)
-    cnt = torch.zeros(5, dtype=torch.int64, device=device or "cuda")
     ext = torch.cuda.ExternalStream(dec.stream())
+    with torch.cuda.stream(ext):      # the zero-fill is ordered on the decoder's own stream, in front of the kernel's atomics
+        cnt = torch.zeros(5, dtype=torch.int64, device=device or "cuda")
     if count:
         dec.simulate_device(cnt.data_ptr(), max_iters, ebn0_db, k_info, n_tx, seed, first, count, early_exit=early_exit)
     with torch.cuda.stream(ext):

@@ -53,8 +53,14 @@ enum {
 enum {
     LDPC_B200_ALGO_SPA = 0,     /* sum-product, src/ECC/Code/LDPC/Reference/Orig.hs:81-92 */
     LDPC_B200_ALGO_MINSUM = 1,  /* normalised min-sum alpha = 3/4, src/ECC/Code/LDPC/Reference/Min.hs:75-89 */
-    LDPC_B200_ALGO_SPA_CM = 2   /* sum-product with the cached StableDiv row product of `ldpc/arraylet-cm`
+    LDPC_B200_ALGO_SPA_CM = 2,  /* sum-product with the cached StableDiv row product of `ldpc/arraylet-cm`
                                    (src/ECC/Code/LDPC/Fast/CachedMult.hs:25-56,248-264); float64 only */
+    /* `ldpc/arraylet` (src/ECC/Code/LDPC/Fast/Arraylet.hs:164-186) and `ldpc/arraylet-min`
+     * (Fast/ArrayletMin.hs:167-192): the check updates of SPA / MINSUM with the posterior associated as
+     * L_j + (ne'[m1] + (ne'[m2] + ...)) (foldRowsMatrixlet, ArrayletMin.hs:104-108,191-192) instead of the right fold
+     * of Orig.hs:95-98.  STREAM engine only (verification statements; decisions equal SPA / MINSUM up to that rounding). */
+    LDPC_B200_ALGO_SPA_ARRAYLET = 3,
+    LDPC_B200_ALGO_MINSUM_ARRAYLET = 4
 };
 enum { LDPC_B200_PREC_FP64 = 0, LDPC_B200_PREC_FP32 = 1 };
 /* STREAM   : any H; messages live in HBM, frame-minor layout, one launch per phase.
@@ -83,7 +89,12 @@ const char *ldpc_b200_last_error(void);
 
 /* device = CUDA ordinal, or -1 for the current device. Idempotent. */
 int ldpc_b200_init(int device);
+/* The Code's `finalize` (Utils.hs:91-103): destroys every decoder and code the host has not destroyed itself and the
+ * replicas cached by ldpc_b200_simulate_multi; all handles are invalid afterwards (destroying one again is a no-op).
+ * The library can be initialised again. */
 void ldpc_b200_shutdown(void);
+/* Number of live code / decoder handles (leak checks in tests and in the host binding's finalize). */
+int ldpc_b200_live_handles(int *codes, int *decoders);
 int ldpc_b200_device_count(void);
 
 /* H as CSR: check m has variables col_idx[row_ptr[m] .. row_ptr[m+1]) in ascending order. Arrays are copied. */

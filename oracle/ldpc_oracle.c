@@ -211,7 +211,11 @@ static void vn_update(const oracle_code *c, const double *L, const double *ne2, 
  *   loop n ne lam | syndrome ok -> lam | n >= maxIterations -> orig_lam | otherwise -> next
  *   result = map hard (...)
  * algo: 0 = sum-product (Orig.hs), 1 = normalised min-sum alpha=3/4 (Min.hs),
- *       2 = sum-product with the cached row product of Fast/CachedMult.hs (same loop, CachedMult.hs:233-243).
+ *       2 = sum-product with the cached row product of Fast/CachedMult.hs (same loop, CachedMult.hs:233-243),
+ *       3 = `ldpc/arraylet` (Fast/Arraylet.hs:164-186) and 4 = `ldpc/arraylet-min` (Fast/ArrayletMin.hs:167-192) in
+ *       edge-list form: the check updates of 0 / 1 with the arraylet association of the posterior,
+ *       L_j + (ne'[m1] + (ne'[m2] + ...)); the circulant-vector transcription of the same two modules is
+ *       arraylet_oracle.c and must agree with these bit for bit.
  * variant: 0 = literal O(d^2) check update, 1 = two-min O(d) (min-sum only).
  * trace_c2v (max_iters*E) / trace_lam (max_iters*N): after iteration t (0-based) the new messages /
  * posteriors are stored at offset t; may be NULL.
@@ -229,10 +233,11 @@ int oracle_decode(const oracle_code *c, int algo, int variant, int max_iters, co
         ok = syndrome_ok(c, lam);
         if (ok) break;
         if (n >= max_iters) break;
+        const int cn_algo = algo == 3 ? 0 : (algo == 4 ? 1 : algo);
         if (algo == 2) cn_update_cached_mult(c, lam, ne, ne2);
-        else if (algo == 1 && variant == 1) cn_update_minsum_twomin(c, lam, ne, ne2);
-        else cn_update_literal(c, algo, lam, ne, ne2);
-        if (algo == 2) vn_update_arraylet(c, llr, ne2, lam);
+        else if (cn_algo == 1 && variant == 1) cn_update_minsum_twomin(c, lam, ne, ne2);
+        else cn_update_literal(c, cn_algo, lam, ne, ne2);
+        if (algo >= 2) vn_update_arraylet(c, llr, ne2, lam);
         else vn_update(c, llr, ne2, lam);
         if (trace_c2v) memcpy(trace_c2v + (size_t)n * E, ne2, sizeof(double) * E);
         if (trace_lam) memcpy(trace_lam + (size_t)n * N, lam, sizeof(double) * N);

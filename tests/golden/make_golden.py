@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from ecc_ldpc_b200 import codes  # noqa: E402
-from oracle import dense_ref  # noqa: E402
+from oracle import arraylet_ref, dense_ref  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -44,9 +44,15 @@ def make(code_name, algo, ebn0_db, max_iters, n_frames, seed, n_tx=None, keep="a
         llr = 2.0 * y / sigma ** 2
         llr[n_tx:] = 0.0                               # unpuncture, Utils.hs:55
         tr = []
-        b, it, cv = dense_ref.ldpc(H, algo, max_iters, llr.tolist(), trace=tr)
+        if algo in ("arraylet", "arraylet-min"):
+            # third statement: the circulant-vector modules Fast/Arraylet.hs / Fast/ArrayletMin.hs (oracle/arraylet_ref.py)
+            b, it, cv = arraylet_ref.ldpc(code.sz, code.shifts, "spa" if algo == "arraylet" else "min", max_iters, llr.tolist(), trace=tr)
+        else:
+            b, it, cv = dense_ref.ldpc(H, algo, max_iters, llr.tolist(), trace=tr)
         llrs.append(llr); bits.append(b); iters.append(it); conv.append(cv)
         def edge_vec(d):
+            if algo in ("arraylet", "arraylet-min"):
+                return np.array(arraylet_ref.matrixlet_to_edge_order(d))
             return np.array([d[(m, int(code.col_idx[e]))] for m in range(code.M)
                              for e in range(code.row_ptr[m], code.row_ptr[m + 1])])
         z_e, z_n = np.zeros(code.E), np.zeros(code.N)
@@ -73,7 +79,7 @@ def make(code_name, algo, ebn0_db, max_iters, n_frames, seed, n_tx=None, keep="a
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["moon", "jpl1024", "mackay", "jpl4096", "cm"]
+    which = sys.argv[1:] or ["moon", "jpl1024", "mackay", "jpl4096", "cm", "arraylet"]
     if "moon" in which:
         make("moon.7.13", "spa", 2.0, 20, 48, 11)
         make("moon.7.13", "min", 2.0, 20, 48, 12)
@@ -90,3 +96,7 @@ if __name__ == "__main__":
     if "cm" in which:   # the cached-product sum-product of Fast/CachedMult.hs:233-264 (dense_ref.ldpc_cached_mult)
         make("moon.7.13", "cm", 2.0, 20, 24, 14)
         make("jpl.1024.4.5", "cm", 3.9, 8, 2, 23, n_tx=1280, keep="ends")
+    if "arraylet" in which:   # `ldpc/arraylet-min` / `ldpc/arraylet` in their own circulant-vector form (arraylet_ref.ldpc)
+        make("jpl.1024.4.5", "arraylet-min", 4.0, 12, 4, 51, n_tx=1280, keep="all")
+        make("jpl.1024.4.5", "arraylet", 3.8, 10, 3, 52, n_tx=1280, keep="ends")
+        make("jpl.4096.4.5", "arraylet-min", 3.8, 10, 1, 53, n_tx=5120, keep="ends")

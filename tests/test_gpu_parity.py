@@ -54,7 +54,7 @@ def test_fp64_stream_matches_golden(fname, gpu_lib, dcodes):
         assert it == g["iters"][f] and cv == bool(g["converged"][f]) and np.array_equal(b, g["bits"][f])
         if it == 0:
             continue
-        if algo == "min":      # bit-exact messages
+        if algo in ("min", "arraylet-min"):      # bit-exact messages (arraylet-min: Fast/ArrayletMin.hs:167-192 order)
             assert np.array_equal(c2v[0], g["c2v_first"][f]) and np.array_equal(c2v[-1], g["c2v_last"][f])
             assert np.array_equal(lam[0], g["lam_first"][f]) and np.array_equal(lam[-1], g["lam_last"][f])
             if "c2v_all" in g.files:
@@ -636,3 +636,161 @@ def test_simulate_counters_pinned(gpu_lib, builtin_codes):
         got = {k: int(c[k]) for k in cs["counters"]}
         assert got == cs["counters"], (cs["code"], cs["algo"], got, cs["counters"])
         dec.close(); dc.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: BASELINE config 3, the four-code parity matrix, the atanh' clamp, the arraylet-order statements
+# ------------------------------------------------------------------------------------------------
+def _fer_interval_ok(fe_gpu, fe_ref, F):
+    p = fe_ref / F
+    half = 1.96 * np.sqrt(max(p * (1 - p), 1.0 / F) / F) + 1.0 / F
+    return abs(fe_gpu / F - p) <= half
+
+
+@pytest.mark.parametrize("algo,F,ebn0", [("min", 2048, 3.15), ("spa", 512, 2.85)])
+def test_config3_jpl4096_50_iterations_early_exit(algo, F, ebn0, gpu_lib, dcodes, builtin_codes, oracles):
+    """BASELINE.json config 3: jpl.4096.4.5 sum-product and min-sum, 50 iterations with syndrome early exit, on the
+    float32 RESIDENT engine against the float64 CPU restatement on identical LLRs, in the waterfall (frames that need
+    most of the 50 iterations and frames that fail are both present).  Bars: decisions identical on >= 99.9 % of the
+    frames, iteration counts equal on >= 99 %, FER inside the restatement's 95 % interval."""
+    code = builtin_codes["jpl.4096.4.5"]
+    llr = awgn_llrs(code, ebn0, F, 50505, 5120)
+    dec = gpu_lib.Decoder(dcodes["jpl.4096.4.5"], algo, "fp32", max_batch=1024)
+    assert dec.engine() == gpu_lib.ENGINE_RESIDENT
+    bits, iters, conv = dec.decode(llr, 50)
+    rb, ri, rc = oracles["jpl.4096.4.5"].decode_batch(algo, 50, llr, variant=1 if algo == "min" else 0)
+    same = (bits == rb).all(axis=1)
+    assert same.mean() >= 0.999, (algo, same.mean())
+    assert (iters == ri).mean() >= 0.99, (algo, (iters == ri).mean())
+    assert 0 < rc.mean() < 1 and (ri[rc == 1] > 20).any()          # the cap of 50 matters: some frames converge after iteration 20
+    K = code.K
+    assert _fer_interval_ok(int(bits[:, :K].any(axis=1).sum()), int(rb[:, :K].any(axis=1).sum()), F)
+    assert abs(int(conv.sum()) - int(rc.sum())) <= max(2, F // 500)
+    dec.close()
+
+
+PARITY_MATRIX = [("jpl.4096.4.5", "min", 5120, 3.25, 4096), ("jpl.4096.4.5", "spa", 5120, 3.0, 1024),
+                 ("jpl.1024.4.5", "min", 1280, 3.4, 16384), ("jpl.1024.4.5", "spa", 1280, 3.2, 4096),
+                 ("1920.1280.3.303", "min", 1920, 1.8, 12288), ("1920.1280.3.303", "spa", 1920, 1.5, 3072),
+                 ("moon.7.13", "spa", 20, 2.0, 131072), ("moon.7.13", "min", 20, 2.0, 131072)]
+
+
+@pytest.mark.parametrize("code_name,algo,n_tx,ebn0,F", PARITY_MATRIX)
+def test_parity_matrix_device_generated_frames(code_name, algo, n_tx, ebn0, F, gpu_lib, dcodes, builtin_codes, oracles):
+    """tools/parity_at_scale.py inside the suite: the four codes x both algorithms, frames generated ON THE DEVICE
+    (Philox, the throughput path's generator), downloaded, and decoded by the float32 production engine (ENGINE_AUTO)
+    and by the float64 CPU restatement.  Decisions identical on >= 99.9 % of the frames, iteration counts on >= 99 %,
+    FER inside the restatement's interval; and the device counters of ldpc_b200_simulate over the same frame range are
+    the counts of those decisions."""
+    code = builtin_codes[code_name]
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=8192)
+    assert dec.engine() in (gpu_lib.ENGINE_RESIDENT, gpu_lib.ENGINE_ONCHIP)
+    same = eq_it = fe_g = fe_r = be_g = it_g = 0
+    for f0 in range(0, F, 8192):
+        n = min(8192, F - f0)
+        buf = gpu_lib.DeviceBuffer(n * code.N * 4)
+        dec.generate_llr(buf.ptr, ebn0, code.K, n_tx, 424242, 1000 + f0, n)
+        dec.sync()
+        llr = buf.download(np.float32, (n, code.N)).astype(np.float64)
+        buf.free()
+        gb, gi, gc = dec.decode(llr, 20)
+        rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=1 if algo == "min" else 0)
+        same += int((gb == rb).all(axis=1).sum()); eq_it += int((gi == ri).sum())
+        fe_g += int(gb[:, :code.K].any(axis=1).sum()); fe_r += int(rb[:, :code.K].any(axis=1).sum())
+        be_g += int(gb[:, :code.K].sum()); it_g += int(gi.sum())
+    assert same / F >= 0.999, (code_name, algo, same, F)
+    assert eq_it / F >= 0.99
+    assert 0 < fe_r < F and _fer_interval_ok(fe_g, fe_r, F)
+    c = dec.simulate(20, ebn0, code.K, n_tx, 424242, 1000, F)
+    assert (c["frames"], c["frame_errors"], c["bit_errors"], c["sum_iters"]) == (F, fe_g, be_g, it_g)
+    dec.close()
+
+
+CLAMP = 2 * 18.714973875118524          # -2 * atanh'(+-1)   (Utils.hs:113-117)
+
+
+def _saturated_frames(code, n_frames, seed, punctured_from=None):
+    """LLRs of magnitude >= 40: tanh(x / 2) rounds to +-1 in float64, so every leave-one-out product of the first
+    iteration is exactly +-1 (or exactly 0 next to a punctured position) and atanh' takes its clamp branch."""
+    rng = np.random.default_rng(seed)
+    llr = np.full((n_frames, code.N), -45.0)
+    for f in range(n_frames):
+        if f % 2:
+            llr[f] = -rng.uniform(40.0, 60.0, code.N)
+        flip = rng.choice(code.N if punctured_from is None else punctured_from, 5 + f, replace=False)
+        llr[f, flip] = -llr[f, flip]
+    if punctured_from is not None:
+        llr[:, punctured_from:] = 0.0
+    return llr
+
+
+@pytest.mark.parametrize("code_name,punct", [("jpl.1024.4.5", None), ("jpl.1024.4.5", 1280), ("moon.7.13", None), ("1920.1280.3.303", None)])
+def test_atanh_clamp_known_answer(code_name, punct, gpu_lib, dcodes, builtin_codes, oracles):
+    """Bug history Reference/Orig.hs:85 ("must cap atanh") as a known-answer test: with |LLR| >= 40 every product of the
+    first sum-product iteration is exactly +-1 (0 on the neighbours of a punctured position), so every message of that
+    iteration is exactly -+2 * 18.714973875118524 (or 0).  The float64 STREAM kernels return exactly those values and
+    equal the restatement; the float32 engines (complement domain, cap 54 ln 2) decide the same bits."""
+    code = builtin_codes[code_name]
+    llr = _saturated_frames(code, 6, 4545, punct)
+    d64 = gpu_lib.Decoder(dcodes[code_name], "spa", "fp64", max_batch=8)
+    for f in range(llr.shape[0]):
+        b, it, cv, c2v, lam = d64.decode_trace(llr[f], 10)
+        ob, oit, ocv, oc2v, olam = oracles[code_name].decode("spa", 10, llr[f], trace=True)
+        assert it == oit and it >= 1 and cv == ocv and np.array_equal(b, ob)
+        first = np.abs(oc2v[0])
+        assert np.isin(first, [0.0, CLAMP]).all() and (first == CLAMP).any()          # the restatement clamps ...
+        if punct is None:
+            assert (first == CLAMP).all()
+        assert np.array_equal(c2v[0], oc2v[0])                                         # ... and the kernel returns the same numbers
+        assert np.array_equal(lam[0], olam[0])
+        assert spa_close(c2v[-1], oc2v[-1]) and spa_close(lam[-1], olam[-1])
+    rb, ri, rc = oracles[code_name].decode_batch("spa", 10, llr)
+    for eng in (gpu_lib.ENGINE_AUTO, gpu_lib.ENGINE_STREAM):
+        d32 = gpu_lib.Decoder(dcodes[code_name], "spa", "fp32", max_batch=8, engine=eng)
+        gb, gi, gc = d32.decode(llr, 10)
+        assert np.array_equal(gb, rb) and np.array_equal(gc, rc) and np.array_equal(gi, ri), (code_name, eng)
+        d32.close()
+    # min-sum has no clamp; the same frames must still decode identically (huge but finite magnitudes)
+    mb, mi, mc = oracles[code_name].decode_batch("min", 10, llr, variant=0)
+    dm = gpu_lib.Decoder(dcodes[code_name], "min", "fp32", max_batch=8)
+    gb, gi, gc = dm.decode(llr, 10)
+    assert np.array_equal(gb, mb) and np.array_equal(gi, mi)
+    d64.close(); dm.close()
+
+
+@pytest.mark.parametrize("code_name,ebn0,n_tx", [("jpl.1024.4.5", 3.7, 1280), ("jpl.4096.4.5", 3.3, 5120)])
+@pytest.mark.parametrize("algo", ["arraylet-min", "arraylet"])
+def test_arraylet_order_statements(code_name, ebn0, n_tx, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """`ldpc/arraylet-min` (Fast/ArrayletMin.hs:167-192) and `ldpc/arraylet` (Fast/Arraylet.hs:164-186) on the STREAM
+    engine in float64, against the circulant-vector restatement of those modules (oracle/arraylet_oracle.c): min-sum
+    messages and posteriors identical in every bit, sum-product within the libm tolerance; decisions and iteration
+    counts of the production float32 engine (Orig/Min order) equal the arraylet statement's on the same frames."""
+    from oracle import oracle
+    code = builtin_codes[code_name]
+    base = "min" if algo == "arraylet-min" else "spa"
+    F = 256 if base == "min" else 64
+    llr = awgn_llrs(code, ebn0 - (0.0 if base == "min" else 0.55), F, 7117, n_tx)
+    a = oracle.ArrayletOracle(code)
+    ab, ai, ac = a.decode_batch(base, 20, llr)
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp64", max_batch=64)
+    assert dec.engine() == gpu_lib.ENGINE_STREAM
+    gb, gi, gc = dec.decode(llr, 20)
+    if base == "min":
+        assert np.array_equal(gb, ab) and np.array_equal(gi, ai) and np.array_equal(gc, ac)
+    else:
+        assert (gb == ab).all(axis=1).mean() >= 0.999 and (gi == ai).mean() >= 0.99
+    for f in range(3):
+        b, it, cv, c2v, lam = dec.decode_trace(llr[f], 20)
+        xb, xit, xcv, xc2v, xlam = a.decode(base, 20, llr[f], trace=True)
+        assert it == xit and cv == xcv and np.array_equal(b, xb)
+        if it and base == "min":
+            assert np.array_equal(c2v, xc2v) and np.array_equal(lam, xlam)
+        elif it:
+            assert spa_close(c2v[0], xc2v[0]) and spa_close(lam[0], xlam[0]) and spa_close(c2v[-1], xc2v[-1])
+    prod = gpu_lib.Decoder(dcodes[code_name], base, "fp32", max_batch=256)
+    pb, pi, pc = prod.decode(llr, 20)
+    assert (pb == ab).all(axis=1).mean() >= 0.999 and (pi == ai).mean() >= 0.99
+    assert 0 < ac.mean() < 1
+    with pytest.raises(gpu_lib.LdpcError):
+        dec.set_engine(gpu_lib.ENGINE_RESIDENT)           # verification statements live on STREAM only
+    dec.close(); prod.close()

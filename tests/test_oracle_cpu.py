@@ -294,3 +294,55 @@ def test_cached_mult_statedness(builtin_codes, oracles):
     for f in range(2):
         bits, it, cv = o.decode("spa_cm", 3, llr[f])
         assert it == 3 and not cv and np.array_equal(bits, (llr[f] > 0).astype(np.uint8))     # hard(orig_lam)
+
+
+# ------------------------------------------------------------------------------------------------
+# Third statement: the arraylet modules in circulant-vector form (oracle/arraylet_oracle.c, oracle/arraylet_ref.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fname", [f for f in _golden_files() if "_arraylet" in f])
+def test_arraylet_c_statement_matches_python_circulant_fixtures(fname, builtin_codes):
+    """oracle/arraylet_oracle.c (Matrixlet of per-circulant vectors, Fast/ArrayletMin.hs:23-114,167-192 and
+    Fast/Arraylet.hs:164-186) reproduces the fixtures written by the pure-Python transcription of the same modules bit
+    for bit: decisions, iteration counts, every message and posterior."""
+    from oracle import oracle
+    code_name, algo, max_iters = _parse(fname)
+    g = golden(fname)
+    a = oracle.ArrayletOracle(builtin_codes[code_name])
+    for f in range(g["llr"].shape[0]):
+        bits, it, cv, c2v, lam = a.decode("spa" if algo == "arraylet" else "min", max_iters, g["llr"][f], trace=True)
+        assert it == g["iters"][f] and cv == bool(g["converged"][f]) and np.array_equal(bits, g["bits"][f])
+        if it:
+            assert np.array_equal(c2v[0], g["c2v_first"][f]) and np.array_equal(c2v[-1], g["c2v_last"][f])
+            assert np.array_equal(lam[0], g["lam_first"][f]) and np.array_equal(lam[-1], g["lam_last"][f])
+        if "c2v_all" in g.files:
+            assert np.array_equal(c2v, g["c2v_all"][f][:it]) and np.array_equal(lam, g["lam_all"][f][:it])
+
+
+@pytest.mark.parametrize("code_name,ebn0,n_tx,frames", [("jpl.1024.4.5", 3.7, 1280, 600), ("jpl.4096.4.5", 3.3, 5120, 160)])
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_arraylet_statement_agrees_with_orig_min_order(code_name, ebn0, n_tx, frames, algo, builtin_codes, oracles):
+    """The arraylet modules differ from Reference/Orig.hs / Min.hs only in the association of the posterior sum
+    (L + (a1 + (a2 + ...)) vs a1 + (a2 + (... + L))): on waterfall frames (late convergence and failures both present)
+    the circulant-vector statement, the edge-list statement of the same association and the Orig/Min-order oracle give
+    the same decisions, iteration counts and flags; the two arraylet statements agree in every message bit."""
+    from oracle import oracle
+    code = builtin_codes[code_name]
+    if algo == "spa":          # sum-product converges ~0.5 dB earlier than the alpha = 3/4 min-sum
+        frames //= 4
+        ebn0 -= 0.55
+    llr = awgn_llrs(code, ebn0, frames, 8080, n_tx)
+    a = oracle.ArrayletOracle(code)
+    ab, ai, ac = a.decode_batch(algo, 20, llr)
+    eb, ei, ec = oracles[code_name].decode_batch("arraylet-min" if algo == "min" else "arraylet", 20, llr)
+    ob, oi, oc = oracles[code_name].decode_batch(algo, 20, llr, variant=0)
+    assert np.array_equal(ab, eb) and np.array_equal(ai, ei) and np.array_equal(ac, ec)
+    assert 0 < oc.mean() < 1 and (oi[oc == 1] >= 8).any()
+    assert np.array_equal(ab, ob) and np.array_equal(ai, oi) and np.array_equal(ac, oc)
+    for f in range(2):
+        x = a.decode(algo, 20, llr[f], trace=True)
+        y = oracles[code_name].decode("arraylet-min" if algo == "min" else "arraylet", 20, llr[f], trace=True)
+        z = oracles[code_name].decode(algo, 20, llr[f], trace=True)
+        assert np.array_equal(x[3], y[3]) and np.array_equal(x[4], y[4])
+        n = min(x[1], z[1])
+        if n:     # same messages up to the few ulp the association moves
+            assert np.allclose(x[4][:n], z[4][:n], rtol=1e-12, atol=1e-12) and np.allclose(x[3][:1], z[3][:1], rtol=0, atol=0)
