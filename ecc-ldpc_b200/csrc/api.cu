@@ -2,6 +2,9 @@
 // stream_engine.cu (any H, HBM-streaming), resident_engine.cu (quasi-cyclic, on-chip) and channel.cu.
 #include "common.cuh"
 #include "philox.cuh"
+namespace ldpc {
+#include "resident_common.cuh"
+}
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -190,6 +193,60 @@ static void channel_params(double ebn0_db, int k_info, int n_tx, float *sigma, f
     double s2 = 1.0 / (2.0 * R * pow(10.0, ebn0_db / 10.0));
     *sigma = (float)sqrt(s2);
     *scale = (float)(2.0 / s2);
+}
+
+// decode_trace on the RESIDENT / ONCHIP engines: one frame, messages of every executed iteration in reference edge order
+template <typename T>
+static int trace_onchip_engines_t(ldpc_b200_decoder *d, int max_iters, const double *llr, double *c2v, double *lam)
+{
+    const ldpc_b200_code *c = d->code;
+    const int N = c->N, E = c->E, kind = resident_kind_of(d);
+    const int NE = kind == 3 ? c->g.oc_se : E;                    // ONCHIP dumps its message slots
+    const size_t rows = (size_t)std::max(max_iters, 1);
+    std::vector<T> h((size_t)N);
+    for (int j = 0; j < N; j++) h[j] = (T)llr[j];                 // the rounding the batched path applies on the device
+    T *d_c2v = nullptr, *d_lam = nullptr;
+    cudaError_t e = cudaMalloc(&d_c2v, rows * NE * sizeof(T));
+    if (e == cudaSuccess) e = cudaMalloc(&d_lam, rows * N * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d->d_in, h.data(), (size_t)N * sizeof(T), cudaMemcpyHostToDevice, d->stream);
+    int rc = e == cudaSuccess ? 0 : cuda_fail(e, "decode_trace: buffers", __FILE__, __LINE__);
+    if (!rc) {
+        begin_timing(d);
+        if (kind == 3) {
+            ResidentParams p = {};
+            p.llr = d->d_in; p.bits = d->d_bits; p.iters = d->d_iters; p.conv = d->d_conv;
+            p.n_frames = 1; p.max_iters = max_iters; p.early_exit = 1; p.n_tx = N;
+            p.trace_c2v = d_c2v; p.trace_lam = d_lam; p.trace_ne = NE;
+            rc = onchip_launch(d, p, d->stream, true);
+        } else {
+            rc = resident_trace(d, max_iters, d->d_in, d->d_bits, d->d_iters, d->d_conv, d_c2v, d_lam);
+        }
+        end_timing(d);
+    }
+    int32_t it = 0;
+    if (!rc) {
+        e = cudaMemcpyAsync(&it, d->d_iters, sizeof it, cudaMemcpyDeviceToHost, d->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "decode_trace: kernel", __FILE__, __LINE__);
+    }
+    if (!rc && it > 0) {
+        std::vector<T> hc((size_t)it * NE), hl((size_t)it * N);
+        e = cudaMemcpy(hc.data(), d_c2v, hc.size() * sizeof(T), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(hl.data(), d_lam, hl.size() * sizeof(T), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "decode_trace: copy back", __FILE__, __LINE__);
+        for (int t = 0; t < it && !rc; t++) {
+            if (c2v) for (int q = 0; q < E; q++) c2v[(size_t)t * E + q] = (double)hc[(size_t)t * NE + (kind == 3 ? c->oc_slot_of_edge[q] : q)];
+            if (lam) for (int j = 0; j < N; j++) lam[(size_t)t * N + j] = (double)hl[(size_t)t * N + (kind == 3 ? c->oc_pos_of_var[j] : j)];
+        }
+    }
+    cudaFree(d_c2v); cudaFree(d_lam);
+    return rc;
+}
+
+static int trace_onchip_engines(ldpc_b200_decoder *d, int max_iters, const double *llr, double *c2v, double *lam)
+{
+    return d->precision == LDPC_B200_PREC_FP64 ? trace_onchip_engines_t<double>(d, max_iters, llr, c2v, lam)
+                                               : trace_onchip_engines_t<float>(d, max_iters, llr, c2v, lam);
 }
 
 }  // namespace ldpc
@@ -396,6 +453,7 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
 {
     if (!d || !reg_remove(g_live_decs, d)) return;
     cudaSetDevice(d->device);
+    mailbox_release(d);
     if (d->stream) cudaStreamSynchronize(d->stream);
     stream_free(d);
     cudaFree(d->d_in); cudaFree(d->d_bits); cudaFree(d->d_iters); cudaFree(d->d_conv); cudaFree(d->d_counters);
@@ -423,6 +481,13 @@ int ldpc_b200_decoder_sync(ldpc_b200_decoder_t *d)
     if (!d) { set_error("decoder_sync: null decoder"); return LDPC_B200_EINVAL; }
     LDPC_CUDA(cudaStreamSynchronize(d->stream));
     return finish_timing(d);
+}
+
+int ldpc_b200_decoder_mailbox_stats(const ldpc_b200_decoder_t *d, uint64_t *launches, uint64_t *frames)
+{
+    if (!d) { set_error("mailbox_stats: null decoder"); return LDPC_B200_EINVAL; }
+    mailbox_stats(d, launches, frames);
+    return 0;
 }
 
 int ldpc_b200_decoder_last_timing(ldpc_b200_decoder_t *d, double *kernel_ms, int64_t *launches)
@@ -574,6 +639,15 @@ static int decode_host(ldpc_b200_decoder_t *d, int max_iters, int n_frames, cons
 {
     if (!d || max_iters < 0 || n_frames < 0 || (n_frames && (!llr || (!bits_bytes && !bits_packed)))) { set_error("decode: bad arguments"); return LDPC_B200_EINVAL; }
     if (n_frames == 0) return 0;
+    if (is_double && n_frames <= MAILBOX_DIRECT_FRAMES && mailbox_enabled() && pick_engine(d) == LDPC_B200_ENGINE_RESIDENT) {
+        // the tester's pattern (one frame per call, Utils.hs:68-69): no copies, no stream synchronisation -- the frame goes
+        // through the mailbox its decoder handle shares with the other handles of the code (mailbox.cu)
+        const int Nn = d->code->N;
+        int rc = mailbox_decode(d, d->engine, max_iters, n_frames, (const double *)llr, in_take > 0 ? in_stride : Nn, in_take > 0 ? in_take : Nn,
+                                bits_bytes, out_take, bits_packed, iters, converged);
+        d->last_ms = 0.0; d->last_launches = 1; d->timing_pending = false;
+        return rc;
+    }
     LDPC_CUDA(cudaSetDevice(d->code->device));
     int rc = ensure_pipe(d, bits_bytes != nullptr);
     if (rc) return rc;
@@ -692,11 +766,18 @@ int ldpc_b200_decode_trace(ldpc_b200_decoder_t *d, int max_iters, const double *
     int rc = ensure_staging(d);
     if (rc) return rc;
     int N = d->code->N, W = words_per_frame(N);
-    LDPC_CUDA(cudaMemcpyAsync(d->d_in, llr, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-    begin_timing(d);
-    rc = stream_decode(d, max_iters, 1, 1, d->d_in, true, d->d_bits, d->d_iters, d->d_conv, c2v, lam);
-    end_timing(d);
-    if (rc) return rc;
+    if (pick_engine(d) == LDPC_B200_ENGINE_RESIDENT) {
+        // the tap of the decoder's OWN kernel: TRACE instance of the compiled RESIDENT specialisation (resident_trace.cu) or
+        // the run-time flag of the ONCHIP kernel; messages come back in the decoder's precision and are widened here
+        rc = trace_onchip_engines(d, max_iters, llr, c2v, lam);
+        if (rc) return rc;
+    } else {
+        LDPC_CUDA(cudaMemcpyAsync(d->d_in, llr, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+        begin_timing(d);
+        rc = stream_decode(d, max_iters, 1, 1, d->d_in, true, d->d_bits, d->d_iters, d->d_conv, c2v, lam);
+        end_timing(d);
+        if (rc) return rc;
+    }
     std::vector<uint32_t> packed(W);
     int32_t it = 0; uint8_t cv = 0;
     LDPC_CUDA(cudaMemcpyAsync(packed.data(), d->d_bits, W * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));

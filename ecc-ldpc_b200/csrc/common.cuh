@@ -54,6 +54,8 @@ struct ldpc_b200_code {
     int device = -1;
     ldpc::DeviceGraph g;          // device copy
     int resident_kind = 0;        // 0 = none, 1 / 2 = compiled RESIDENT specialisation, 3 = run-time table ONCHIP kernel
+    // ONCHIP placement, host copy (message tap: slot of reference edge e, position of variable j)
+    std::vector<int32_t> oc_slot_of_edge, oc_pos_of_var;
 };
 
 namespace ldpc {
@@ -100,6 +102,8 @@ struct ldpc_b200_decoder {
     cudaStream_t d2h_stream = nullptr;
     // RESIDENT engine scratch
     unsigned int *res_work = nullptr;   // persistent-CTA work counter
+    int oc_blocks_per_sm = 0, oc_n_sm = 0;   // ONCHIP: cached occupancy of this decoder's persistent grid
+    void *mbox = nullptr;               // the mailbox this handle shares with the other handles of its code (mailbox.cu)
     void *res_conv_buf = nullptr;       // max_batch x N float, when float64 LLRs feed the fp32 kernel
     size_t res_conv_bytes = 0;
 };
@@ -130,11 +134,28 @@ int resident_simulate(ldpc_b200_decoder *d, int max_iters, int early_exit, float
                       int k_info, int n_tx, uint64_t seed, uint64_t first_frame, uint64_t n_frames,
                       uint64_t *d_counters);
 
+// message tap on the decoder's own kernel (resident_trace.cu): one frame, d_c2v [max_iters][E] / d_lam [max_iters][N] in T
+int resident_trace(ldpc_b200_decoder *d, int max_iters, const void *d_llr, uint32_t *d_bits, int32_t *d_iters, uint8_t *d_conv,
+                   void *d_c2v, void *d_lam);
+// latency instances for small batches (resident_latency.cu)
+struct ResidentParams;
+bool resident_latency_supports(const ldpc_b200_decoder *d);
+int resident_latency_launch(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream);
+// small batch on `stream` with a static one-pass grid through the production instance (fp64, or no latency instance)
+int resident_static_launch(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream);
+
 // ---- on-chip engine for arbitrary codes (onchip_engine.cu) ----
 int onchip_build_tables(ldpc_b200_code *c);
 bool onchip_fits(const ldpc_b200_code *c, int precision);
-struct ResidentParams;
-int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p);
+int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream = nullptr, bool static_grid = false);
+
+// ---- mailbox: one-frame-per-call path shared by all decoder handles of a code (mailbox.cu) ----
+bool mailbox_enabled();
+int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames, const double *llr, int stride, int take,
+                   uint8_t *bits_bytes, int out_take, uint32_t *bits_packed, int32_t *iters, uint8_t *converged);
+void mailbox_release(ldpc_b200_decoder *d);
+void mailbox_stats(const ldpc_b200_decoder *d, uint64_t *launches, uint64_t *frames);
+static const int MAILBOX_DIRECT_FRAMES = 4;      // host-buffer calls of at most this many frames take the mailbox
 
 // ---- channel (channel.cu) ----
 int channel_generate(ldpc_b200_decoder *d, float sigma, float llr_scale, int n_tx, uint64_t seed,

@@ -23,12 +23,15 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include <algorithm>
+#include <atomic>
 #include <utility>
 
 namespace ldpc {
 
 #include "bp_tree.cuh"
 #include "resident_common.cuh"
+
+struct OnchipLaunch { cudaStream_t stream; bool static_grid; };
 
 struct OnchipGeom {
     int TPF, FPC, SE, CD;     // threads per frame, frames per CTA, message slots per frame, staged entries per variable record
@@ -63,16 +66,27 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
     __syncthreads();
 
     FrameCounters cnt;
-    for (;;) {
-        if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
-        bar_sync(bar, TPF);
-        const unsigned int f = s_next[slot];
+    for (int round = 0;; round++) {
+        unsigned int f;
+        if (!p.work) {                       // static assignment (small latency-bound launches, see resident_kernel.cuh)
+            if (round) break;
+            f = blockIdx.x * geo.FPC + slot;
+        } else {
+            if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
+            bar_sync(bar, TPF);
+            f = s_next[slot];
+        }
         if (f >= p.n_frames) break;
+        const unsigned int fi = p.use_map ? p.slot_map[f] : f;      // output index: the frame itself or its mailbox slot
 
         // ---- frame in: lam = L (Orig.hs:58), ne = 0 (Orig.hs:64-65) ----
         if (p.llr) {
-            const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;
+            const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)fi * N;
             for (int j = tf; j < N; j += TPF) { T v = src[j]; int q = varPos[j]; L[q] = v; lam[q] = v; }
+        } else if (p.llr64) {
+            // the reference's float64 vector rounded to T; positions >= take are punctured (Utils.hs:55)
+            const double *src = p.llr64 + (size_t)fi * p.llr64_stride;
+            for (int j = tf; j < N; j += TPF) { T v = j < p.llr64_take ? (T)src[j] : (T)0; int q = varPos[j]; L[q] = v; lam[q] = v; }
         } else {
             for (int q4 = tf; q4 < (N + 3) / 4; q4 += TPF) {
                 float nz[4];
@@ -135,15 +149,20 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                     const int j = 32 * w + lane;
                     unsigned int word = __ballot_sync(0xffffffffu, j < N && src[varPos[j < N ? j : 0]] > (T)0);
                     if (lane == 0) {
-                        if (p.bits) p.bits[(size_t)f * W + w] = word;
+                        if (p.bits) p.bits[(size_t)fi * W + w] = word;
                         int lo = 32 * w;
                         if (lo + 32 <= p.k_info) errs += __popc(word);
                         else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
                     }
                 }
                 if (tf == 0) {
-                    if (p.iters) p.iters[f] = n;
-                    if (p.conv) p.conv[f] = conv ? 1 : 0;
+                    if (p.iters) p.iters[fi] = n;
+                    if (p.conv) p.conv[fi] = conv ? 1 : 0;
+                }
+                if (p.done) {                    // mailbox: completion flag behind a system-scope fence (arrays in mapped host memory)
+                    __threadfence_system();
+                    bar_sync(bar, TPF);
+                    if (tf == 0) *reinterpret_cast<volatile unsigned int *>(p.done + fi) = p.done_seq;
                 }
                 if (p.counters) {
                     bool anyerr = bar_or(bar, TPF, errs != 0);
@@ -154,6 +173,10 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                 }
             }
             if (n == p.max_iters || (done && p.early_exit)) break;
+            if (p.trace_c2v && f == 0) {         // message tap (run-time flag: the messages live in shared memory, nothing else changes)
+                T *out = reinterpret_cast<T *>(p.trace_c2v) + (size_t)n * p.trace_ne;
+                for (int e = tf; e < SE; e += TPF) out[e] = ne[e];      // slot order; the host maps slots back to reference edges
+            }
 
             // ---- variable phase (Orig.hs:95-98): lam'[j] = ne'[m1] + (ne'[m2] + (... + (ne'[mk] + L_j))), by position ----
             for (int q = tf; q < N; q += TPF) {
@@ -174,6 +197,10 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
                 lam[q] = acc;
             }
             bar_sync(bar, TPF);
+            if (p.trace_lam && f == 0) {
+                T *out = reinterpret_cast<T *>(p.trace_lam) + (size_t)n * N;
+                for (int q = tf; q < N; q += TPF) out[q] = lam[q];      // position order; reordered by the host
+            }
         }
     }
 
@@ -188,6 +215,7 @@ __global__ void __launch_bounds__(512) k_onchip(DeviceGraph g, ResidentParams p,
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 
+static constexpr int ONCHIP_MAX_DEVICES = 64;
 static const size_t ONCHIP_MAX_CTA_BYTES = 113 * 1024;      // tables + frames of a CTA when two CTAs share an SM
 
 // Proper 32-colouring of the edges of a bipartite multigraph with maximum degree <= 32 (left node ga[e], right node
@@ -330,6 +358,8 @@ int onchip_build_tables(ldpc_b200_code *c)
     LDPC_CUDA(cudaMalloc(&g.col_slot, sizeof(int32_t) * E));
     LDPC_CUDA(cudaMemcpy(g.col_slot, cs.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
     g.oc_tab_elems = (int)tab.size(); g.oc_se = SE; g.oc_cd = CD; g.oc_cdr = CDR;
+    c->oc_slot_of_edge.assign(slot.begin(), slot.end());
+    c->oc_pos_of_var.assign(pos.begin(), pos.end());
     return 0;
 }
 
@@ -356,59 +386,84 @@ static bool onchip_geometry(const ldpc_b200_code *c, size_t es, OnchipGeom *out)
 bool onchip_fits(const ldpc_b200_code *c, int precision) { return onchip_geometry(c, elem_size(precision), nullptr); }
 
 template <typename T, int ALGO, int MAXD, bool REG, int CDR>
-static int onchip_launch_t(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo)
+static int onchip_launch_t(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo, const OnchipLaunch &oc)
 {
     auto kern = k_onchip<T, ALGO, MAXD, REG, CDR>;
     const int threads = geo.FPC * geo.TPF;
     const size_t smem = geo.table_bytes + (size_t)geo.FPC * geo.frame_elems * sizeof(T) + geo.FPC * sizeof(unsigned int);
     int blocks_per_sm = 0, n_sm = 0;
-    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem));
-    LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->code->device));
-    if (blocks_per_sm < 1) { set_error("ONCHIP kernel does not fit on this device"); return LDPC_B200_EUNSUPPORTED; }
-    if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
-    LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), d->stream));
-    p.work = d->res_work;
+    // the dynamic shared-memory limit is a per-device function attribute: raised (never lowered) when a launch needs more;
+    // the occupancy of the persistent grid is cached per decoder (one code, one geometry)
+    static std::atomic<int> cfg_smem[ONCHIP_MAX_DEVICES];
+    const int dev = d->code->device;
+    if (dev < 0 || dev >= ONCHIP_MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return LDPC_B200_EINVAL; }
+    if (cfg_smem[dev].load(std::memory_order_acquire) < (int)smem) {
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        cfg_smem[dev].store((int)smem, std::memory_order_release);
+    }
+    if (!oc.static_grid) {
+        if (!d->oc_blocks_per_sm) {
+            LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->oc_blocks_per_sm, kern, threads, smem));
+            LDPC_CUDA(cudaDeviceGetAttribute(&d->oc_n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        blocks_per_sm = d->oc_blocks_per_sm; n_sm = d->oc_n_sm;
+        if (blocks_per_sm < 1) { d->oc_blocks_per_sm = 0; set_error("ONCHIP kernel does not fit on this device"); return LDPC_B200_EUNSUPPORTED; }
+    }
     unsigned int groups = (p.n_frames + geo.FPC - 1) / geo.FPC;
-    unsigned int grid = std::min<unsigned int>(groups, (unsigned int)(blocks_per_sm * n_sm));
+    unsigned int grid;
+    if (oc.static_grid) {
+        p.work = nullptr;
+        grid = groups;
+    } else {
+        if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
+        LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), oc.stream));
+        p.work = d->res_work;
+        grid = std::min<unsigned int>(groups, (unsigned int)(blocks_per_sm * n_sm));
+    }
     if (grid == 0) return 0;
-    kern<<<grid, threads, smem, d->stream>>>(d->code->g, p, geo);
+    kern<<<grid, threads, smem, oc.stream>>>(d->code->g, p, geo);
     d->launches++;
     LDPC_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <typename T, int ALGO>
-static int onchip_launch_d(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo)
+static int onchip_launch_d(ldpc_b200_decoder *d, ResidentParams &p, const OnchipGeom &geo, const OnchipLaunch &oc)
 {
     // (regular instances only for the small row classes: a regular code of row degree exactly 18 or 32 takes the masked form)
     const bool reg = d->code->g.row_regular != 0;
     const bool c4 = d->code->g.oc_cdr == 4;
     switch (d->code->g.row_ell_d) {
     case 4:
-        if (reg) return c4 ? onchip_launch_t<T, ALGO, 4, true, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 4, true, 8>(d, p, geo);
-        return c4 ? onchip_launch_t<T, ALGO, 4, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 4, false, 8>(d, p, geo);
+        if (reg) return c4 ? onchip_launch_t<T, ALGO, 4, true, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 4, true, 8>(d, p, geo, oc);
+        return c4 ? onchip_launch_t<T, ALGO, 4, false, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 4, false, 8>(d, p, geo, oc);
     case 8:
-        if (reg) return c4 ? onchip_launch_t<T, ALGO, 8, true, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 8, true, 8>(d, p, geo);
-        return c4 ? onchip_launch_t<T, ALGO, 8, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 8, false, 8>(d, p, geo);
-    case 18: return c4 ? onchip_launch_t<T, ALGO, 18, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 18, false, 8>(d, p, geo);
-    case 32: return c4 ? onchip_launch_t<T, ALGO, 32, false, 4>(d, p, geo) : onchip_launch_t<T, ALGO, 32, false, 8>(d, p, geo);
+        if (reg) return c4 ? onchip_launch_t<T, ALGO, 8, true, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 8, true, 8>(d, p, geo, oc);
+        return c4 ? onchip_launch_t<T, ALGO, 8, false, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 8, false, 8>(d, p, geo, oc);
+    case 18: return c4 ? onchip_launch_t<T, ALGO, 18, false, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 18, false, 8>(d, p, geo, oc);
+    case 32: return c4 ? onchip_launch_t<T, ALGO, 32, false, 4>(d, p, geo, oc) : onchip_launch_t<T, ALGO, 32, false, 8>(d, p, geo, oc);
     default: set_error("ONCHIP engine: check degree above 32"); return LDPC_B200_EUNSUPPORTED;
     }
 }
 
-int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p)
+int onchip_launch(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream, bool static_grid)
 {
     OnchipGeom geo;
+    OnchipLaunch oc = {stream ? stream : d->stream, static_grid};
+    if (static_grid) {
+        // latency launches: ONE frame per CTA, so that a handful of frames spreads over as many SMs instead of sharing one
+        if (!onchip_geometry(d->code, elem_size(d->precision), &geo)) { set_error("ONCHIP engine: the frame state of this code does not fit shared memory"); return LDPC_B200_EUNSUPPORTED; }
+        geo.FPC = 1;
+    } else
     if (!onchip_geometry(d->code, elem_size(d->precision), &geo)) { set_error("ONCHIP engine: the frame state of this code does not fit shared memory"); return LDPC_B200_EUNSUPPORTED; }
     if (d->algo == LDPC_B200_ALGO_SPA) {
         if (d->precision != LDPC_B200_PREC_FP32) { set_error("ONCHIP engine: sum-product is float32 only"); return LDPC_B200_EUNSUPPORTED; }
-        return onchip_launch_d<float, LDPC_B200_ALGO_SPA>(d, p, geo);
+        return onchip_launch_d<float, LDPC_B200_ALGO_SPA>(d, p, geo, oc);
     }
     if (d->algo != LDPC_B200_ALGO_MINSUM) { set_error("ONCHIP engine: unsupported algorithm"); return LDPC_B200_EUNSUPPORTED; }
-    return d->precision == LDPC_B200_PREC_FP64 ? onchip_launch_d<double, LDPC_B200_ALGO_MINSUM>(d, p, geo)
-                                               : onchip_launch_d<float, LDPC_B200_ALGO_MINSUM>(d, p, geo);
+    return d->precision == LDPC_B200_PREC_FP64 ? onchip_launch_d<double, LDPC_B200_ALGO_MINSUM>(d, p, geo, oc)
+                                               : onchip_launch_d<float, LDPC_B200_ALGO_MINSUM>(d, p, geo, oc);
 }
 
 }  // namespace ldpc

@@ -1,0 +1,586 @@
+// resident_kernel.cuh -- device code of the RESIDENT engine (see resident_engine.cu for the design notes); included inside
+// namespace ldpc by the translation units that instantiate it: resident_engine.cu (production instances),
+// resident_latency.cu (one-frame-per-CTA-pair latency instances) and resident_trace.cu (message-tap instances).
+#pragma once
+
+// Compile-time layout of the per-thread message registers: the rows of a part, in order, each with row_deg slots.
+template <class C> struct QcMap {
+    static __host__ __device__ constexpr int reg_base(int r)
+    {
+        int h = C::half_of_row[r], b = 0;
+        for (int q = 0; q < C::HR; q++) {
+            int rr = C::half_rows[h][q];
+            if (rr == r) return b;
+            b += C::row_deg[rr];
+        }
+        return -1;
+    }
+    static __host__ __device__ constexpr int part_edges(int h)
+    {
+        int b = 0;
+        for (int q = 0; q < C::HR; q++) b += C::row_deg[C::half_rows[h][q]];
+        return b;
+    }
+    static __host__ __device__ constexpr int max_part_edges()
+    {
+        int m = 0;
+        for (int h = 0; h < C::NP; h++) m = part_edges(h) > m ? part_edges(h) : m;
+        return m;
+    }
+    static constexpr int NEH = max_part_edges();
+    static constexpr int N = C::BC * C::SZ;
+    // edge (r, k) is the LAST link of its column's chain (the first block row of the column): the thread that finishes
+    // the new posterior of that variable is also the one that reads it for edge (r, k) in the next check phase
+    static __host__ __device__ constexpr bool is_final_edge(int r, int k)
+    {
+        int c = C::row_col[r][k];
+        return C::col_row_desc[c][C::col_deg[c] - 1] == r;
+    }
+    static __host__ __device__ constexpr int local_row(int r)       // index of row r inside its part
+    {
+        int h = C::half_of_row[r];
+        for (int q = 0; q < C::HR; q++) if (C::half_rows[h][q] == r) return q;
+        return -1;
+    }
+};
+
+// Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
+// BLK = SZ*sizeof(T) bytes and BLK-aligned, so only the low log2(BLK) bits rotate: one add + one bit-select.
+template <class C, typename T, int S>
+__device__ __forceinline__ uint32_t rot(uint32_t P)
+{
+    constexpr uint32_t MASK = C::SZ * sizeof(T) - 1;
+    if constexpr (S == 0) return P;
+    else {
+        uint32_t y = P + S * (uint32_t)sizeof(T), z;
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(z) : "r"(P), "r"(y), "n"(MASK));   // (P & ~MASK) | (y & MASK)
+        return z;
+    }
+}
+
+template <typename T> __device__ __forceinline__ T minus34() { return (T)-0.75; }
+
+// Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
+// round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
+// zero (punctured LLR, or a sum that cancels) is +0.0 in mu, and mu is never -0.0 (x + y = -0 needs both operands
+// -0, and negL = 0 - L is never -0).  Hence hard(lam) = (lam > 0) = sign bit of mu, and the syndrome parity of a
+// check row is the xor of the sign bits of its mu's: half a LOP3 per edge instead of a compare per edge.
+
+// Check-node phase for the rows of part H. P = shared address of mu[i]. Returns true if any of this thread's
+// checks is unsatisfied by hard(lam).
+// FOLD (min-sum instances): for the edges that are the last link of their column's chain, the variable phase (or the
+// frame prologue) has already left x = ne + mu in the message register and the sign of mu in fpar[row], so the check
+// phase neither loads nor adds for them: 44 of the 156 shared-memory loads of an iteration disappear.
+template <class C, typename T, int H, int ALGO, bool FOLD>
+__device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
+{
+    typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
+    typename F::B unsat = 0;
+    static_for<C::HR>([&](auto qi) {
+        constexpr int r = C::half_rows[H][decltype(qi)::value];
+        constexpr int d = C::row_deg[r];
+        constexpr int base = QcMap<C>::reg_base(r);
+        typename F::B par = 0;
+        if constexpr (FOLD) { par = fpar[decltype(qi)::value]; fpar[decltype(qi)::value] = 0; }
+        static_for<d>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            constexpr int c = C::row_col[r][k];
+            constexpr int s = C::row_shift[r][k];
+            if constexpr (!(FOLD && QcMap<C>::is_final_edge(r, k))) {
+                T m = F::template lds<c * BLK>(rot<C, T, s>(P));
+                par ^= F::bits(m);
+                ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
+            }
+        });
+        unsat |= par;
+        if constexpr (ALGO == LDPC_B200_ALGO_MINSUM) {
+            // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
+            BoxTree<T, 0, d> tree;
+            tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
+            tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = F::mul(minus34<T>(), others); });
+        } else if constexpr (sizeof(T) == 4) {
+            // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form
+            uint32_t sgn = 0;
+            static_for<d>([&](auto ki) { sgn ^= __float_as_uint(ne[base + decltype(ki)::value]); });
+            sgn = ~sgn;                                                // leading minus times the product of ALL signs
+            BoxTree<float, 0, d, OpCompl> tree;
+            tree.build([&](auto ki) { return spa_compl(ne[base + decltype(ki)::value]); });
+            tree.down_root([&](auto ki, float others) {
+                constexpr int k = decltype(ki)::value;
+                // own sign removed from the product: sgn ^ sign(x_k); magnitude >= 0 so its sign bit is free
+                ne[base + k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+            });
+        }
+    });
+    return unsat & F::SIGN;        // non-zero sign bit(s): an unsatisfied check (one bit per packed frame)
+}
+
+// Exclusive compile-time dispatch on a run-time index: a binary tree of (warp-uniform) branches whose leaves call
+// fn(integral_constant<idx>).
+template <int LO, int HI, class Fn>
+__device__ __forceinline__ void dispatch_index(int sel, Fn &&fn)
+{
+    if constexpr (HI - LO == 1) fn(std::integral_constant<int, LO>{});
+    else {
+        constexpr int MID = (LO + HI) / 2;
+        if (sel < MID) dispatch_index<LO, MID>(sel, fn);
+        else dispatch_index<MID, HI>(sel, fn);
+    }
+}
+
+// The "big" rows of a code are those of maximum degree (18 for the AR4JA codes); every part carries the same number.
+template <class C> struct BigRows {
+    static __host__ __device__ constexpr int count(int h)
+    {
+        int n = 0;
+        for (int q = 0; q < C::HR; q++) n += C::row_deg[C::half_rows[h][q]] == C::MAXD;
+        return n;
+    }
+    static __host__ __device__ constexpr int row(int h, int j)
+    {
+        for (int q = 0; q < C::HR; q++)
+            if (C::row_deg[C::half_rows[h][q]] == C::MAXD && j-- == 0) return C::half_rows[h][q];
+        return -1;
+    }
+    static __host__ __device__ constexpr bool uniform()
+    {
+        for (int h = 1; h < C::NP; h++) if (count(h) != count(0)) return false;
+        return true;
+    }
+    static constexpr int NB = count(0);
+};
+
+// Sum-product check phase with ONE copy of the arithmetic of a big row.  Fully unrolled, the sum-product loop body
+// is ~100 KB of SASS (30 instructions per edge, 156 circulants): it does not fit the 32 KB instruction cache and the
+// kernel was fetch-bound (ncu: 43 % of the stall samples `no_instruction`).  Here the per-row code is only what
+// depends on the circulant table -- gather x = ne + mu at the start, the sign/magnitude merge into ne' at the end --
+// selected by a warp-uniform branch tree; the complement / tree / logarithm arithmetic of a degree-MAXD row exists once
+// and is shared by all big rows of all parts.  The small rows (degree 3) stay inline.
+template <class C>
+__device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NEH], uint32_t P, int h)
+{
+    typedef FB<float> F;
+    constexpr int BLK = C::SZ * sizeof(float), D = C::MAXD, NB = BigRows<C>::NB;
+    static_assert(BigRows<C>::uniform(), "parts must carry the same number of maximum-degree rows");
+    uint32_t unsat = 0;
+    dispatch_index<0, C::NP>(h, [&](auto hi) {
+        constexpr int H = decltype(hi)::value;
+        static_for<C::HR>([&](auto qi) {
+            constexpr int r = C::half_rows[H][decltype(qi)::value];
+            constexpr int d = C::row_deg[r];
+            constexpr int base = QcMap<C>::reg_base(r);
+            if constexpr (d != D) {
+                uint32_t par = 0, sgn = 0;
+                static_for<d>([&](auto ki) {
+                    constexpr int k = decltype(ki)::value;
+                    float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                    par ^= F::bits(m);
+                    ne[base + k] = F::add(ne[base + k], m);
+                    sgn ^= F::bits(ne[base + k]);
+                });
+                unsat |= par;
+                sgn = ~sgn;
+                BoxTree<float, 0, d, OpCompl> tree;
+                tree.build([&](auto ki) { return spa_compl(ne[base + decltype(ki)::value]); });
+                tree.down_root([&](auto ki, float others) {
+                    constexpr int k = decltype(ki)::value;
+                    ne[base + k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                });
+            }
+        });
+    });
+#pragma unroll 1
+    for (int j = 0; j < NB; j++) {
+        float xs[D];
+        uint32_t par = 0;
+        const int sel = h * NB + j;
+        dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
+            constexpr int idx = decltype(ci)::value;
+            constexpr int r = BigRows<C>::row(idx / NB, idx % NB);
+            constexpr int base = QcMap<C>::reg_base(r);
+            static_for<D>([&](auto ki) {
+                constexpr int k = decltype(ki)::value;
+                float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                par ^= F::bits(m);
+                xs[k] = F::add(ne[base + k], m);                  // x = ne + mu   (Orig.hs:84)
+            });
+        });
+        unsat |= par;
+        // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form.
+        // The sign of x_k rides in the sign bit of its (non-negative) complement: the tree reads magnitudes through
+        // operand modifiers, so x itself is dead after this point (18 registers less at the widest place).
+        uint32_t sgn = 0;
+        static_for<D>([&](auto ki) { sgn ^= __float_as_uint(xs[decltype(ki)::value]); });
+        // cap with the sign "leading minus times the product of ALL signs" (still to be multiplied by sign(x_k))
+        const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
+        static_for<D>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            xs[k] = __uint_as_float(__float_as_uint(spa_compl(xs[k])) | (__float_as_uint(xs[k]) & 0x80000000u));
+        });
+        BoxTree<float, 0, D, OpComplAbs> tree;
+        tree.build([&](auto ki) { return xs[decltype(ki)::value]; });
+        tree.down_root([&](auto ki, float others) {
+            constexpr int k = decltype(ki)::value;
+            // min(|lg2((2-c)/c)|, cap) with sign = sign(cap_s) xor sign(x_k): one LOP3 + one FMNMX.XORSIGN
+            xs[k] = F::box(spa_mag_lg2(others), __uint_as_float(cap_s ^ (__float_as_uint(xs[k]) & 0x80000000u)));
+        });
+        dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
+            constexpr int idx = decltype(ci)::value;
+            constexpr int base = QcMap<C>::reg_base(BigRows<C>::row(idx / NB, idx % NB));
+            static_for<D>([&](auto ki) { ne[base + decltype(ki)::value] = xs[decltype(ki)::value] * 0.69314718055994531f; });
+        });
+    }
+    return unsat & F::SIGN;
+}
+
+// Syndrome only (used for the test after the last iteration).
+template <class C, typename T, int H>
+__device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
+{
+    typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
+    typename F::B unsat = 0;
+    static_for<C::HR>([&](auto qi) {
+        constexpr int r = C::half_rows[H][decltype(qi)::value];
+        constexpr int d = C::row_deg[r];
+        typename F::B par = 0;
+        static_for<d>([&](auto ki) {
+            constexpr int k = decltype(ki)::value;
+            par ^= F::bits(F::template lds<C::row_col[r][k] * BLK>(rot<C, T, C::row_shift[r][k]>(P)));
+        });
+        unsat |= par;
+    });
+    return unsat & F::SIGN;
+}
+
+// Variable-node stage Q for part H.  Column c builds mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the
+// exact negation of Orig.hs:95-98, one link per stage from the innermost (last block row) outwards; col_stage
+// says which link runs in which stage.  negL sits N*sizeof(T) bytes after mu.
+template <class C, typename T, int H, int Q, bool FOLD>
+__device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
+{
+    typedef FB<T> F;
+    constexpr int BLK = C::SZ * sizeof(T);
+    constexpr int NEGL = QcMap<C>::N * sizeof(T);
+    // Two passes: every load of the stage is issued before the first store.  The accesses are volatile asm and keep
+    // their program order, so a fused load-subtract-store per link would serialise the stage on shared-memory latency.
+    T acc[C::BC];
+    static_for<C::BC>([&](auto ci) {
+        constexpr int c = decltype(ci)::value;
+        constexpr int step = C::col_stage[c][Q];          // which link of column c's chain runs in this stage
+        if constexpr (step >= 0) {
+            constexpr int r = C::col_row_desc[c][step];
+            if constexpr (C::half_of_row[r] == H) {
+                constexpr int k = C::col_k_desc[c][step];
+                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
+                acc[c] = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * BLK>(a);
+            }
+        }
+    });
+    static_for<C::BC>([&](auto ci) {
+        constexpr int c = decltype(ci)::value;
+        constexpr int step = C::col_stage[c][Q];
+        if constexpr (step >= 0) {
+            constexpr int r = C::col_row_desc[c][step];
+            if constexpr (C::half_of_row[r] == H) {
+                constexpr int k = C::col_k_desc[c][step];
+                constexpr int e = QcMap<C>::reg_base(r) + k;
+                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
+                const T val = F::sub(acc[c], ne[e]);
+                F::template sts<c * BLK>(a, val);
+                if constexpr (FOLD && step == C::col_deg[c] - 1) {
+                    // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
+                    ne[e] = F::add(ne[e], val);                                  // x of the next check phase
+                    fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
+                }
+            }
+        }
+    });
+}
+
+// Reference edge index of edge (block row r, check position i, k-th circulant of the row): rows in ascending order,
+// ascending column inside a row (the order Orig.hs:82-92 visits the ones of H) -- used by the message tap.
+template <class C> struct RefEdge {
+    static __host__ __device__ constexpr int row_base(int r)
+    {
+        int b = 0;
+        for (int q = 0; q < r; q++) b += C::row_deg[q] * C::SZ;
+        return b;
+    }
+};
+
+// Decode of one frame by the threads of part H (the iteration loop is instantiated per part so that no dispatch
+// happens inside it; all parts execute the same sequence of named barriers).
+// H >= 0: instance for part H.  H = -1: one instance for all parts with the part h as a run-time value (the sum-product
+// form, whose big-row arithmetic is shared: cn_phase_spa_looped); table-dependent phases branch on h (warp-uniform).
+// TRACE: message tap of launch frame 0 (ldpc_b200_decode_trace).  (The output index of the frame -- f or its mailbox slot --
+// and the staging row of the packed decisions are recomputed where the frame finishes: nothing extra stays live in the loop.)
+template <class C, typename T, int H, int ALGO, bool TRACE, int FPC>
+__device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned int f, const T *mu, const T *negL, uint32_t P,
+                                             int bar, int tf, int lane, FrameCounters &cnt, int h = H)
+{
+    typedef QcMap<C> Mp;
+    constexpr int N = Mp::N, TPF = C::NP * C::SZ, WPF = TPF / 32, W = N / 32;
+    const int wif = tf >> 5;
+    constexpr bool FOLD = (H >= 0) && ALGO == LDPC_B200_ALGO_MINSUM && RES_FOLD;
+    T ne[Mp::NEH];
+    typename FB<T>::B fpar[C::HR];
+#pragma unroll
+    for (int e = 0; e < Mp::NEH; e++) ne[e] = (T)0;               // orig_ne = 0 (Orig.hs:64-65)
+#pragma unroll
+    for (int q = 0; q < C::HR; q++) fpar[q] = 0;
+    if constexpr (FOLD) {
+        // prologue of the fold: x = 0 + mu and the sign of mu for the last-link edges (what the variable phase leaves
+        // behind from the second iteration on)
+        static_for<C::HR>([&](auto qi) {
+            constexpr int r = C::half_rows[H][decltype(qi)::value];
+            static_for<C::row_deg[r]>([&](auto ki) {
+                constexpr int k = decltype(ki)::value;
+                if constexpr (Mp::is_final_edge(r, k)) {
+                    T m = FB<T>::template lds<C::row_col[r][k] * C::SZ * (int)sizeof(T)>(rot<C, T, C::row_shift[r][k]>(P));
+                    ne[Mp::reg_base(r) + k] = m;
+                    fpar[decltype(qi)::value] ^= FB<T>::bits(m);
+                }
+            });
+        });
+    }
+
+    bool done = false;
+    for (int n = 0;; n++) {
+        bool finished_now = false, conv = false;
+        if (!(done && n == p.max_iters)) {
+            bool unsat;
+            if constexpr (H >= 0) {
+                unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO, FOLD>(ne, fpar, P)) != 0;
+            } else {
+                typename FB<T>::B u = 0;
+                if (n == p.max_iters) dispatch_index<0, C::NP>(h, [&](auto hi) { u = synd_phase<C, T, decltype(hi)::value>(P); });
+                else u = cn_phase_spa_looped<C>(ne, P, h);
+                unsat = u != 0;
+            }
+            bool any = bar_or(bar, TPF, unsat);
+            if (!done && (!any || n == p.max_iters)) { finished_now = true; conv = !any; }
+        }
+        if (finished_now) {
+            // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
+            done = true;
+            const T *src = conv ? mu : negL;
+            const unsigned int fi = p.use_map ? p.slot_map[f] : f;
+            uint32_t *obuf = reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC * 2 - 2 * (bar - 1) - 1) * N + (size_t)(bar - 1) * N);
+            unsigned int errs = 0;
+            for (int w = wif; w < W; w += WPF) {
+                unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] < (T)0);   // lam > 0 <=> -lam < 0
+                if (lane == 0) {
+                    if (p.done) obuf[w] = word;
+                    else if (p.bits) p.bits[(size_t)fi * W + w] = word;
+                    int lo = 32 * w;
+                    if (lo + 32 <= p.k_info) errs += __popc(word);
+                    else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
+                }
+            }
+            if (p.done) {
+                // mailbox: the packed decisions leave in full lines (the arrays are in mapped host memory: one PCIe write per
+                // 128 bytes instead of one per word), then the completion flag behind a system-scope fence
+                bar_sync(bar, TPF);
+                for (int w = tf; w < W; w += TPF) p.bits[(size_t)fi * W + w] = obuf[w];
+                if (tf == 0) { if (p.iters) p.iters[fi] = n; if (p.conv) p.conv[fi] = conv ? 1 : 0; }
+                __threadfence_system();
+                bar_sync(bar, TPF);
+                if (tf == 0) *reinterpret_cast<volatile unsigned int *>(p.done + fi) = p.done_seq;
+            } else if (tf == 0) {
+                if (p.iters) p.iters[fi] = n;
+                if (p.conv) p.conv[fi] = conv ? 1 : 0;
+            }
+            if (p.counters) {
+                bool anyerr = bar_or(bar, TPF, errs != 0);
+                cnt.berr += errs;
+                if (tf == 0) { cnt.frames++; cnt.ferr += anyerr; cnt.iters += n; cnt.unconv += !conv; }
+            } else if (!p.early_exit) {
+                bar_sync(bar, TPF);          // snapshot reads of mu before the next stage-0 writes
+            }
+        }
+        if (n == p.max_iters || (done && p.early_exit)) break;
+
+        if constexpr (TRACE) {
+            // message tap: ne' of this iteration in reference edge order (Orig.hs:81-92 / Min.hs:75-87), before the last-link
+            // fold of the variable phase turns some registers into the next x
+            if (f == 0 && p.trace_c2v) {
+                T *out = reinterpret_cast<T *>(p.trace_c2v) + (size_t)n * p.trace_ne;
+                const int i = tf % C::SZ;
+                dispatch_index<0, C::NP>(h, [&](auto hi) {
+                    constexpr int HH = decltype(hi)::value;
+                    static_for<C::HR>([&](auto qi) {
+                        constexpr int r = C::half_rows[HH][decltype(qi)::value];
+                        constexpr int d = C::row_deg[r];
+                        static_for<d>([&](auto ki) { out[RefEdge<C>::row_base(r) + i * d + decltype(ki)::value] = ne[Mp::reg_base(r) + decltype(ki)::value]; });
+                    });
+                });
+            }
+        }
+
+        // ---- variable phase ----
+        static_for<C::MAXCD>([&](auto qi) {
+            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value, FOLD>(ne, fpar, P);
+            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value, false>(ne, fpar, P); });
+            bar_sync(bar, TPF);
+        });
+
+        if constexpr (TRACE) {
+            if (f == 0 && p.trace_lam) {        // lam' = -mu (Orig.hs:95-98); every stage ended behind a barrier
+                T *out = reinterpret_cast<T *>(p.trace_lam) + (size_t)n * N;
+                for (int j = tf; j < N; j += TPF) out[j] = -mu[j];
+            }
+        }
+    }
+}
+
+// MINB: resident CTAs per SM the register allocation is bounded for (production: 2 for float32; latency instances: 1,
+// which lets the NP = 4 form keep its messages in registers at 512 threads).
+template <class C, typename T, int FPC, int ALGO, int MINB, bool TRACE>
+__global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(ResidentParams p)
+{
+    typedef QcMap<C> Mp;
+    typedef FB<T> F;
+    constexpr int N = Mp::N, SZ = C::SZ, TPF = C::NP * SZ;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF;
+    const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31;
+    const int bar = slot + 1;
+    T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;      // negated posterior, see above
+    T *negL = mu + N;                                                    // negated channel LLRs
+    // staging row of the NEXT frame's LLRs (host-supplied frames only): fetched by one bulk copy while this frame decodes;
+    // in mailbox mode (no prefetch) the same row stages the packed decisions
+    T *stage = reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N + (size_t)slot * N;
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 3 * N);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(s_next + ((FPC + 1) & ~1)) + slot;
+    const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
+    const bool prefetch = p.llr != nullptr && p.llr_bulk && p.work != nullptr;
+    constexpr uint32_t ROWB = N * sizeof(T);
+
+    FrameCounters cnt;
+    uint32_t phase = 0;
+    if (prefetch) {
+        if (tf == 0) {
+            mbar_init(mbar, 1);
+            const unsigned int nxt = atomicAdd(p.work, 1u);
+            s_next[slot] = nxt;
+            if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+        }
+        bar_sync(bar, TPF);
+    }
+    for (int round = 0;; round++) {
+        unsigned int f;
+        if (!p.work) {
+            // static assignment (small latency-bound launches): one frame per slot, no work counter to reset or contend on
+            if (round) break;
+            f = blockIdx.x * FPC + slot;
+        } else {
+            if (!prefetch) {
+                if (tf == 0) s_next[slot] = atomicAdd(p.work, 1u);
+                bar_sync(bar, TPF);
+            }
+            f = s_next[slot];
+        }
+        if (f >= p.n_frames) break;
+        const unsigned int fi = p.use_map ? p.slot_map[f] : f;
+
+        // ---- frame in: negL = 0 - L, mu = negL ----
+        if (prefetch) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, stage[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
+            if (tf == 0) {
+                const unsigned int nxt = atomicAdd(p.work, 1u);
+                s_next[slot] = nxt;             // read at the top of the next round, many barriers from here
+                if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+            }
+        } else if (p.llr) {
+            const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)fi * N;
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            bar_sync(bar, TPF);
+        } else if (p.llr64) {
+            // the reference's float64 vector, rounded to T exactly as the host-side conversion would; unpuncture (Utils.hs:55)
+            const double *src = p.llr64 + (size_t)fi * p.llr64_stride;
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, j < p.llr64_take ? (T)src[j] : (T)0); negL[j] = v; mu[j] = v; }
+            bar_sync(bar, TPF);
+        } else {
+            for (int g = tf; g < N / 4; g += TPF) {
+                float nz[4];
+                awgn4(p.seed, p.first_frame + f, (uint32_t)g, nz);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int j = 4 * g + q;
+                    T v = F::sub((T)0, (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0);
+                    negL[j] = v; mu[j] = v;
+                }
+            }
+            bar_sync(bar, TPF);
+        }
+
+        if constexpr (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4 && RES_SPA_LOOPED) {
+            decode_frame<C, T, -1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt, h);
+        } else if constexpr (C::NP == 2) {
+            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+        } else {
+            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 1) decode_frame<C, T, 1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 2) decode_frame<C, T, 2, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 3, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+        }
+        // all smem reads of this frame are done before the next frame's values arrive: decode_frame ends behind a barrier
+    }
+
+    if (p.counters) {
+        if (lane == 0 && cnt.berr) atomicAdd(&p.counters[2], cnt.berr);
+        if (tf == 0 && cnt.frames) {
+            atomicAdd(&p.counters[0], cnt.frames); atomicAdd(&p.counters[1], cnt.ferr);
+            atomicAdd(&p.counters[3], cnt.iters); atomicAdd(&p.counters[4], cnt.unconv);
+        }
+    }
+}
+
+static constexpr int MAX_DEVICES = 64;
+
+// Launch of one instance.  Function attributes (dynamic shared-memory limit, carve-out) are PER DEVICE, so the "already
+// configured" cache is keyed by the device of the code, not by the calling thread; concurrent first launches write the
+// same values.  static_grid: one CTA per group of FPC frames and no work counter (small latency-bound launches).
+template <class C, typename T, int FPC, int ALGO, int MINB, bool TRACE>
+static int launch_instance(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream, bool static_grid)
+{
+    typedef QcMap<C> Mp;
+    auto kern = k_resident<C, T, FPC, ALGO, MINB, TRACE>;
+    size_t smem = (size_t)FPC * 3 * Mp::N * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
+    static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
+    static std::atomic<int> cfg_bps[MAX_DEVICES], cfg_sm[MAX_DEVICES];
+    const int dev = d->code->device;
+    if (dev < 0 || dev >= MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return LDPC_B200_EINVAL; }
+    int blocks_per_sm = cfg_bps[dev].load(std::memory_order_acquire), n_sm = cfg_sm[dev].load(std::memory_order_relaxed);
+    if (!blocks_per_sm) {
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        LDPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FPC * C::NP * C::SZ, smem));
+        LDPC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (blocks_per_sm < 1) { set_error("RESIDENT kernel does not fit on this device"); return LDPC_B200_EUNSUPPORTED; }
+        cfg_sm[dev].store(n_sm, std::memory_order_relaxed);
+        cfg_bps[dev].store(blocks_per_sm, std::memory_order_release);
+    }
+    unsigned int groups = (p.n_frames + FPC - 1) / FPC;
+    unsigned int grid;
+    if (static_grid) {
+        p.work = nullptr;
+        grid = groups;
+    } else {
+        if (!d->res_work) LDPC_CUDA(cudaMalloc(&d->res_work, sizeof(unsigned int)));
+        LDPC_CUDA(cudaMemsetAsync(d->res_work, 0, sizeof(unsigned int), stream));
+        p.work = d->res_work;
+        grid = std::min<unsigned int>(groups, (unsigned int)(blocks_per_sm * n_sm));
+    }
+    if (grid == 0) return 0;
+    kern<<<grid, FPC * C::NP * C::SZ, smem, stream>>>(p);
+    d->launches++;
+    LDPC_CUDA(cudaGetLastError());
+    return 0;
+}

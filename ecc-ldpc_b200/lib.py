@@ -26,7 +26,7 @@ EXPORTS = [
     "ldpc_b200_code_destroy", "ldpc_b200_code_info", "ldpc_b200_decoder_create",
     "ldpc_b200_decoder_set_engine", "ldpc_b200_decoder_engine", "ldpc_b200_decoder_destroy",
     "ldpc_b200_decode", "ldpc_b200_decode_punctured", "ldpc_b200_decode_f32", "ldpc_b200_decode_trace", "ldpc_b200_decode_device",
-    "ldpc_b200_decoder_sync", "ldpc_b200_decoder_last_timing", "ldpc_b200_generate_llr",
+    "ldpc_b200_decoder_sync", "ldpc_b200_decoder_last_timing", "ldpc_b200_decoder_mailbox_stats", "ldpc_b200_generate_llr",
     "ldpc_b200_simulate", "ldpc_b200_simulate_device", "ldpc_b200_simulate_multi", "ldpc_b200_simulate_multi_release",
     "ldpc_b200_count_errors", "ldpc_b200_malloc", "ldpc_b200_free",
     "ldpc_b200_malloc_host", "ldpc_b200_free_host", "ldpc_b200_memcpy_h2d", "ldpc_b200_memcpy_d2h",
@@ -91,6 +91,7 @@ def load():
     L.ldpc_b200_decode_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.ldpc_b200_decoder_sync.argtypes = [vp]
     L.ldpc_b200_decoder_last_timing.argtypes = [vp, C.POINTER(f64), C.POINTER(C.c_int64)]
+    L.ldpc_b200_decoder_mailbox_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.ldpc_b200_generate_llr.argtypes = [vp, f64, i32, i32, u64, u64, i32, vp, vp]
     L.ldpc_b200_simulate.argtypes = [vp, i32, i32, f64, i32, i32, u64, u64, u64, C.POINTER(Counters)]
     L.ldpc_b200_simulate_device.argtypes = [vp, i32, i32, f64, i32, i32, u64, u64, u64, vp]
@@ -293,6 +294,12 @@ class Decoder:
         n = C.c_int64(0)
         check(load().ldpc_b200_decoder_last_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def mailbox_stats(self):
+        """(launches, frames) served so far by the mailbox this handle shares with the other handles of its code."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(load().ldpc_b200_decoder_mailbox_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def generate_llr(self, d_llr, ebn0_db, k_info, n_tx, seed, first_frame, n_frames, d_codewords=None):
         check(load().ldpc_b200_generate_llr(self.h, ebn0_db, k_info, n_tx, seed, first_frame, n_frames, d_codewords, d_llr))

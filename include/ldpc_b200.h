@@ -126,7 +126,9 @@ int ldpc_b200_decode_punctured(ldpc_b200_decoder_t *dec, int max_iters, int n_fr
 
 /* One frame, with the messages of every executed iteration t (0-based): c2v[t*E + e] = ne'[edge e] in
  * reference edge order (row-major, ascending column), lam[t*N + j] = lam'[j]. Arrays hold max_iters rows.
- * Always runs the STREAM engine (its operation order is the reference's). */
+ * Runs the engine the decoder decodes with (ldpc_b200_decoder_engine): the STREAM kernels, the message-tap instance of the
+ * compiled RESIDENT kernel (registers dumped in reference edge order) or the ONCHIP kernel with its tap enabled; values of
+ * a float32 decoder are the float32 messages widened to double. */
 int ldpc_b200_decode_trace(ldpc_b200_decoder_t *dec, int max_iters, const double *llr, double *c2v,
                            double *lam, int32_t *iters, uint8_t *bits, uint8_t *converged);
 
@@ -138,6 +140,12 @@ int ldpc_b200_decode_trace(ldpc_b200_decoder_t *dec, int max_iters, const double
 int ldpc_b200_decode_device(ldpc_b200_decoder_t *dec, int max_iters, int early_exit, int n_frames,
                             const void *d_llr, uint32_t *d_bits_packed, int32_t *d_iters, uint8_t *d_converged);
 int ldpc_b200_decoder_sync(ldpc_b200_decoder_t *dec);
+/* Host-buffer calls of one to four frames on a RESIDENT / ONCHIP decoder -- the `decode` of the reference's tester, one
+ * frame per call from several threads (Utils.hs:62-69) -- go through a MAILBOX shared by all decoder handles of the code:
+ * slots in mapped host memory, frames of concurrent callers coalesced into one launch of a latency-oriented kernel, no
+ * copies and no stream synchronisation.  Same results as the batched path.  LDPC_B200_MAILBOX=0 in the environment
+ * disables it.  This reports how many launches served how many frames through this decoder's mailbox so far. */
+int ldpc_b200_decoder_mailbox_stats(const ldpc_b200_decoder_t *dec, uint64_t *launches, uint64_t *frames);
 /* Device time (ms) of the decode kernels of the last decode* call on this decoder, and launches it made. */
 int ldpc_b200_decoder_last_timing(ldpc_b200_decoder_t *dec, double *kernel_ms, int64_t *launches);
 

@@ -647,11 +647,12 @@ def _fer_interval_ok(fe_gpu, fe_ref, F):
     return abs(fe_gpu / F - p) <= half
 
 
-@pytest.mark.parametrize("algo,F,ebn0", [("min", 2048, 3.15), ("spa", 512, 2.85)])
-def test_config3_jpl4096_50_iterations_early_exit(algo, F, ebn0, gpu_lib, dcodes, builtin_codes, oracles):
+@pytest.mark.parametrize("algo,F,ebn0,waterfall", [("min", 2048, 2.9, True), ("min", 2048, 3.15, False), ("spa", 512, 2.6, True), ("spa", 512, 3.0, False)])
+def test_config3_jpl4096_50_iterations_early_exit(algo, F, ebn0, waterfall, gpu_lib, dcodes, builtin_codes, oracles):
     """BASELINE.json config 3: jpl.4096.4.5 sum-product and min-sum, 50 iterations with syndrome early exit, on the
-    float32 RESIDENT engine against the float64 CPU restatement on identical LLRs, in the waterfall (frames that need
-    most of the 50 iterations and frames that fail are both present).  Bars: decisions identical on >= 99.9 % of the
+    float32 RESIDENT engine against the float64 CPU restatement on identical LLRs: in the 50-iteration waterfall (2.9 dB
+    min-sum / 2.6 dB sum-product: frames that need most of the 50 iterations and frames that fail are both present) and
+    at 3.0-3.15 dB where every frame converges, many of them after iteration 20.  Bars: decisions identical on >= 99.9 % of the
     frames, iteration counts equal on >= 99 %, FER inside the restatement's 95 % interval."""
     code = builtin_codes["jpl.4096.4.5"]
     llr = awgn_llrs(code, ebn0, F, 50505, 5120)
@@ -662,7 +663,9 @@ def test_config3_jpl4096_50_iterations_early_exit(algo, F, ebn0, gpu_lib, dcodes
     same = (bits == rb).all(axis=1)
     assert same.mean() >= 0.999, (algo, same.mean())
     assert (iters == ri).mean() >= 0.99, (algo, (iters == ri).mean())
-    assert 0 < rc.mean() < 1 and (ri[rc == 1] > 20).any()          # the cap of 50 matters: some frames converge after iteration 20
+    assert (ri[rc == 1] > 20).any()                                # the cap of 50 matters: frames converge after iteration 20
+    if waterfall:
+        assert 0.5 < rc.mean() < 0.99
     K = code.K
     assert _fer_interval_ok(int(bits[:, :K].any(axis=1).sum()), int(rb[:, :K].any(axis=1).sum()), F)
     assert abs(int(conv.sum()) - int(rc.sum())) <= max(2, F // 500)
@@ -794,3 +797,175 @@ def test_arraylet_order_statements(code_name, ebn0, n_tx, algo, gpu_lib, dcodes,
     with pytest.raises(gpu_lib.LdpcError):
         dec.set_engine(gpu_lib.ENGINE_RESIDENT)           # verification statements live on STREAM only
     dec.close(); prod.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: message tap on the production engines (north_star: fp64 1e-9 / fp32 1e-4 per-edge), the mailbox
+# ------------------------------------------------------------------------------------------------
+def _msg_errors(got, ref):
+    """(max |got - ref| / max(|ref|, 1), fraction of entries with |got - ref| <= 1e-4 |ref|): the first is the bar of the
+    suite (x = ne - lam cancels, so the error of a small message is set by the size of its operands, not its own), the
+    second says how much of the trace meets the plain relative reading of "within 1e-4"."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    err = np.abs(got - ref)
+    return float((err / np.maximum(np.abs(ref), 1.0)).max()), float((err <= 1e-4 * np.abs(ref)).mean())
+
+
+TAP_CASES = [("jpl.1024.4.5", 1280, 4.1, 2), ("jpl.4096.4.5", 5120, 3.9, 2), ("1920.1280.3.303", None, 3.0, 3), ("moon.7.13", None, 4.0, 3)]
+
+
+@pytest.mark.parametrize("code_name,n_tx,ebn0,want_engine", TAP_CASES)
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_message_tap_production_engines_fp32_within_1e4(code_name, n_tx, ebn0, want_engine, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """ldpc_b200_decode_trace on the engines that produce the throughput numbers: the float32 RESIDENT kernels (message
+    registers dumped in reference edge order by the TRACE instance) and the float32 ONCHIP kernel (shared-memory messages),
+    against the float64 restatement on the same (float32-rounded) LLRs.  Per-edge messages and posteriors of the first
+    iterations within 1e-4 (relative to max(|ref|, 1)); decisions, iteration counts and flags equal.  Sum-product
+    messages are compared where the reference itself resolves them: below 30 in magnitude (above, its float64 product
+    1 - p is a small multiple of 2^-53 and its own messages move in steps of up to 0.7)."""
+    code = builtin_codes[code_name]
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=4)
+    assert dec.engine() == want_engine
+    llr = awgn_llrs(code, ebn0 - (0.4 if algo == "spa" else 0.0), 5, 2718, n_tx).astype(np.float32).astype(np.float64)
+    worst, frac, checked = 0.0, 1.0, 0
+    for f in range(llr.shape[0]):
+        b, it, cv, c2v, lam = dec.decode_trace(llr[f], 8)
+        rb, rit, rcv, rc2v, rlam = oracles[code_name].decode(algo, 8, llr[f], variant=0, trace=True)
+        assert it == rit and cv == rcv and np.array_equal(b, rb), (code_name, algo, f, it, rit)
+        assert c2v.shape == rc2v.shape and lam.shape == rlam.shape
+        gb, gi, gc = dec.decode(llr[f:f + 1], 8)                  # the tap does not change the decode
+        assert np.array_equal(gb[0], b) and gi[0] == it
+        if not it:
+            continue
+        n = min(it, 6)
+        if algo == "spa":
+            m = np.abs(rc2v[:n]) < 30.0
+            e1, f1 = _msg_errors(c2v[:n][m], rc2v[:n][m])
+            ml = np.abs(rlam[:n]) < 30.0
+            e2, f2 = _msg_errors(lam[:n][ml], rlam[:n][ml])
+        else:
+            e1, f1 = _msg_errors(c2v[:n], rc2v[:n])
+            e2, f2 = _msg_errors(lam[:n], rlam[:n])
+        worst, frac, checked = max(worst, e1, e2), min(frac, f1, f2), checked + 1
+    assert checked >= 3
+    assert worst <= 1e-4, (code_name, algo, worst)
+    assert frac >= 0.99, (code_name, algo, frac)
+    dec.close()
+
+
+@pytest.mark.parametrize("code_name,n_tx,ebn0,force_onchip", [("jpl.1024.4.5", 1280, 3.8, False), ("jpl.4096.4.5", 5120, 3.5, False),
+                                                              ("1920.1280.3.303", None, 2.4, False), ("jpl.1024.4.5", 1280, 3.8, True)])
+def test_message_tap_fp64_minsum_bit_exact(code_name, n_tx, ebn0, force_onchip, gpu_lib, dcodes, builtin_codes, oracles):
+    """The float64 instances of the on-chip kernels follow the reference's operation order: every message and posterior of
+    every iteration, read out of the RESIDENT registers / ONCHIP shared memory, equals the restatement's in every bit
+    (well inside the 1e-9 bar of the verification mode)."""
+    code = builtin_codes[code_name]
+    eng = gpu_lib.ENGINE_ONCHIP if force_onchip else gpu_lib.ENGINE_AUTO
+    dec = gpu_lib.Decoder(dcodes[code_name], "min", "fp64", max_batch=4, engine=eng)
+    assert dec.engine() in (gpu_lib.ENGINE_RESIDENT, gpu_lib.ENGINE_ONCHIP)
+    llr = awgn_llrs(code, ebn0, 4, 1618, n_tx)
+    for f in range(4):
+        b, it, cv, c2v, lam = dec.decode_trace(llr[f], 20)
+        rb, rit, rcv, rc2v, rlam = oracles[code_name].decode("min", 20, llr[f], variant=0, trace=True)
+        assert it == rit and cv == rcv and np.array_equal(b, rb)
+        assert np.array_equal(c2v, rc2v) and np.array_equal(lam, rlam)
+    dec.close()
+
+
+@pytest.mark.parametrize("code_name,algo,prec,n_tx,ebn0", [("jpl.4096.4.5", "min", "fp32", 5120, 3.4), ("jpl.4096.4.5", "spa", "fp32", 5120, 3.0),
+                                                        ("jpl.1024.4.5", "min", "fp32", 1280, 3.6), ("jpl.1024.4.5", "min", "fp64", 1280, 3.6),
+                                                        ("1920.1280.3.303", "min", "fp32", None, 2.2), ("moon.7.13", "spa", "fp32", None, 3.0)])
+def test_mailbox_tester_pattern_concurrent_single_frame_calls(code_name, algo, prec, n_tx, ebn0, gpu_lib, dcodes, builtin_codes, oracles):
+    """The reference tester's calling pattern (Utils.hs:53,62-69): `maxThreadCount` decoder handles on one code, each host
+    thread calling `decode` with ONE frame at a time, concurrently.  Those calls go through the shared mailbox (coalesced
+    launches of the latency kernels): every result equals the batched path's bit for bit (same arithmetic), which in turn
+    meets the 99.9 % bar against the restatement; and frames were coalesced (fewer launches than frames)."""
+    import threading
+    code = builtin_codes[code_name]
+    T, calls = 16, 24
+    llr = awgn_llrs(code, ebn0, T * calls, 4321, n_tx)
+    batch = gpu_lib.Decoder(dcodes[code_name], algo, prec, max_batch=T * calls)
+    bb, bi, bc = batch.decode(llr, 20)                                   # batched path (n_frames > 4)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 20, llr, variant=0)
+    assert (bb == rb).all(axis=1).mean() >= 0.999
+    decs = [gpu_lib.Decoder(dcodes[code_name], algo, prec, max_batch=1) for _ in range(T)]
+    out_b = np.zeros_like(bb); out_i = np.zeros_like(bi); out_c = np.zeros_like(bc)
+    errs = []
+
+    def work(t):
+        try:
+            for c in range(calls):
+                f = t * calls + c
+                b, it, cv = decs[t].decode(llr[f:f + 1], 20)
+                out_b[f], out_i[f], out_c[f] = b[0], it[0], cv[0]
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    assert np.array_equal(out_b, bb) and np.array_equal(out_i, bi) and np.array_equal(out_c, bc)
+    launches, frames = decs[0].mailbox_stats()
+    assert frames == T * calls and 1 <= launches <= frames
+    # two- and four-frame calls take the mailbox too; ragged max_iters values are grouped per launch
+    b2, i2, c2 = decs[1].decode(llr[:4], 20)
+    assert np.array_equal(b2, bb[:4]) and np.array_equal(i2, bi[:4])
+    b3, i3, c3 = decs[2].decode(llr[:2], 3)
+    r3 = oracles[code_name].decode_batch(algo, 3, llr[:2], variant=0)
+    assert (b3 == r3[0]).all(axis=1).mean() >= 0.5 and np.array_equal(i3, r3[1])
+    [d.close() for d in decs]
+    batch.close()
+
+
+def test_mailbox_ecc_record_single_frame(gpu_lib, builtin_codes, oracles):
+    """ECC.decode of the record (one received vector per call, punctured tail, first K bits back) through the mailbox ==
+    the restatement's wrapper (Utils.hs:55,68-72)."""
+    from ecc_ldpc_b200 import ecc
+    (e,) = ecc.match("ldpc/b200-minsum/jpl.4096.4.5/20/4/5", max_batch=1)
+    code = builtin_codes["jpl.4096.4.5"]
+    rx = awgn_llrs(code, 3.6, 12, 777, 5120)[:, :5120]
+    for f in range(12):
+        out, flag = e.decode(rx[f])
+        ref, rflag, it, cv = oracles["jpl.4096.4.5"].ecc_decode("min", 20, 4096, 5120, rx[f])
+        assert flag and np.array_equal(out, ref)
+    e.close()
+
+
+def test_shutdown_releases_everything(gpu_lib):
+    """ldpc_b200_shutdown = the Code's `finalize`: live handles (codes, decoders, mailboxes, simulate_multi replicas) are
+    destroyed, destroying them again is a no-op, and the library can be initialised and used again.  Runs in its own
+    process: shutting the library down would invalidate the handles the other tests' fixtures hold."""
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = textwrap.dedent("""
+        import ctypes as C, sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from conftest import awgn_llrs
+        from ecc_ldpc_b200 import codes, lib
+        L = lib.load(); lib.init(0)
+        nc, nd = C.c_int(), C.c_int()
+        code = codes.load_builtin("jpl.1024.4.5")
+        dc = lib.DeviceCode(code)
+        decs = [lib.Decoder(dc, "min", "fp32", max_batch=1) for _ in range(3)]
+        llr = awgn_llrs(code, 4.0, 1, 5, 1280)
+        want = decs[0].decode(llr, 20)                       # creates the mailbox
+        big = decs[1].decode(np.repeat(llr, 8, axis=0), 20)  # and the batched staging
+        lib.simulate_multi(dc, 1, "min", "fp32", 64, 20, 3.5, code.K, 1280, 1, 0, 64)
+        L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
+        assert (nc.value, nd.value) == (2, 4), (nc.value, nd.value)      # + the replica of simulate_multi
+        L.ldpc_b200_shutdown()
+        L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
+        assert (nc.value, nd.value) == (0, 0)
+        [d.close() for d in decs]; dc.close()                # stale handles: ignored
+        lib.init(0)
+        dc2 = lib.DeviceCode(code)
+        d2 = lib.Decoder(dc2, "min", "fp32", max_batch=1)
+        got = d2.decode(llr, 20)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        d2.close(); dc2.close()
+        print("SHUTDOWN-OK")
+    """) % (root, os.path.join(root, "tests"))
+    out = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SHUTDOWN-OK" in out.stdout, out.stderr[-2000:]
