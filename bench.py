@@ -38,6 +38,22 @@ METRIC = "decoded_info_gbit_per_s"
 UNIT = "Gbit/s"
 
 
+def workload_config(frames_per_step_per_gpu, n_values_per_frame):
+    """The `config` object of the JSON line: the SAME dictionary on both arms (the CPU arm times a bounded sample of every
+    step of this workload and says so in `cpu_baseline.sample`)."""
+    return {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
+            "frames_per_step_per_gpu": frames_per_step_per_gpu,
+            "frames": "Philox4x32-10 keyed by seed %d, stream = global frame index; rank r owns frames [r*B, (r+1)*B)" % SEED,
+            "l2": "inputs larger than L2 (%.0f MB of LLRs per step per GPU)" % (frames_per_step_per_gpu * n_values_per_frame * 4 / 1e6),
+            "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step"}
+
+
+def so_sha256():
+    import hashlib
+    from ecc_ldpc_b200 import lib
+    return hashlib.sha256(open(lib.SO_PATH, "rb").read()).hexdigest()
+
+
 def alg_bytes_per_frame(code, iters, w=4):
     """B_alg = iters * w * (3E + 3N) + w * N_tx + K/8."""
     return iters * w * (3 * code.E + 3 * code.N) + w * N_TX + code.K // 8
@@ -78,22 +94,22 @@ class ClockSampler(threading.Thread):
 
 def reference_arm(args):
     """CPU arm: the C restatement of the reference decoder (oracle/, kind 'port' -- the Haskell reference cannot be
-    built in this image) on all host cores, same code / algorithm / iteration cap / Eb/N0 as the GPU arm."""
+    built in this image) on all host cores, on the GPU arm's workload: same code / algorithm / iteration cap / Eb/N0 and
+    the SAME frames (the Philox stream of the device generator, drawn on the host by ecc-ldpc_b200/philox_host.py).
+    Each step = a bounded sample of the step's frames_per_step_per_gpu frames (the first `--cpu-frames`, default 64 per
+    core), so that the run ends within minutes; frames/s do not depend on the sample size."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from ecc_ldpc_b200 import codes
+    from ecc_ldpc_b200 import codes, philox_host
     from oracle import oracle
     code = codes.load_builtin(CODE)
     orc = oracle.Oracle(code)
     cores = oracle.lib().oracle_max_threads()
     frames = args.cpu_frames or 64 * cores
-    rng = np.random.default_rng(SEED)
-    sigma = np.sqrt(1.0 / (2 * (code.K / N_TX) * 10 ** (EBN0_WORST / 10)))
-    llr = 2.0 * (-1.0 + sigma * rng.standard_normal((frames, code.N))) / sigma ** 2
-    llr[:, N_TX:] = 0.0
+    llr = philox_host.awgn_llrs(code.N, EBN0_WORST, code.K, N_TX, SEED, 0, frames).astype(np.float64)
     for _ in range(args.warmup):
-        orc.decode_batch("min", MAX_ITERS, llr[: max(cores, 8)], variant=1, threads=cores)
+        orc.decode_batch("min", MAX_ITERS, llr[: max(4 * cores, 8)], variant=1, threads=cores)
     t0 = time.perf_counter()
     its = 0
     for _ in range(args.steps):
@@ -106,12 +122,12 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
-                   "frames_per_step": frames, "avg_iters": its / (frames * args.steps)},
+        "config": workload_config(args.frames, code.N),
+        "avg_iters": its / (frames * args.steps),
         "edge_updates_per_s": fps * (its / (frames * args.steps)) * code.E,
         "frames_per_s": fps,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d frames x %d steps, two-minimum O(E) check update, one frame per thread" % (frames, args.steps)},
+                         "sample": "every step decodes the first %d of the step's %d frames (same Philox frames as the GPU arm, float64), %d steps after %d warm-up passes; two-minimum O(E) check update, one frame per thread, %d threads" % (frames, args.frames, args.steps, args.warmup, cores)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,6 +196,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")       # host-side rendezvous that leaves the GPUs idle (see the simulate_multi leg)
     lib.init(local)
 
     code = codes.load_builtin(CODE)
@@ -263,15 +280,21 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B * b_alg / (k_ms * 1e-3) / 1e9
-    traffic, ncu_static = None, None
+    # roofline.traffic: dram bytes of ONE launch of the decode kernel from an `ncu --set full` capture, written to
+    # profiles/traffic.json by tools/ncu_traffic.py together with the SHA-256 of the libldpc_b200.so that was profiled.
+    # A capture of another build is NOT reported: traffic = null and the reason is printed.
+    traffic, ncu_static, traffic_note = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("dram_bytes_per_launch_per_frame")
-        ncu_static = tj.get("ncu")
-        if traffic is not None:
-            traffic = traffic * B
-    except Exception:
-        pass
+        if tj.get("so_sha256") != so_sha256():
+            traffic_note = "profiles/traffic.json was captured from another build of libldpc_b200.so (sha256 %s...); re-run tools/ncu_traffic.py" % str(tj.get("so_sha256"))[:12]
+            print("bench.py: " + traffic_note, file=sys.stderr)
+        else:
+            traffic = tj["dram_bytes_per_launch_per_frame"] * B
+            ncu_static = tj.get("ncu")
+            traffic_note = "ncu capture %s of kernel %s, same build" % (tj.get("capture"), tj.get("kernel"))
+    except Exception as ex:
+        traffic_note = "no usable profiles/traffic.json (%r)" % (ex,)
 
     # ---------------- e2e: the reference-facing plugin call, host buffers in and out ----------------
     # ECC record `decode` (Utils.hs:62-72) of "ldpc/b200-minsum/jpl.4096.4.5/20/4/5": c_length = 5120 received float64
@@ -312,8 +335,65 @@ def main():
            "d2h_bytes_per_step": Be * code.K, "frames_per_step": Be, "matches_device_path": e2e_same,
            "api": "ldpc_b200_ecc_decode = ECC.decode of ldpc/b200-minsum/%s/%d/4/5 (float64 received LLRs in pinned host memory; message bits back)" % (CODE, MAX_ITERS)}
 
-    # ---------------- extra operating points with early exit (reference semantics) ----------------
+    # ---------------- what the platform can move: concurrent pinned H2D copies on all ranks ----------------
+    # the e2e leg is bound by the host -> device hop (41 KB of float64 per frame); this is its ceiling at N ranks
     extra = {}
+    cp_bytes = 256 << 20
+    h_big = torch.empty(cp_bytes, dtype=torch.uint8).pin_memory()
+    d_big = torch.empty(cp_bytes, dtype=torch.uint8, device="cuda")
+    d_big.copy_(h_big, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(8):
+        d_big.copy_(h_big, non_blocking=True)
+    c1.record()
+    barrier()
+    cms = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device="cuda")
+    own_gbs = 8 * cp_bytes / (float(cms.item()) * 1e-3) / 1e9
+    if world > 1:
+        dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+    agg_gbs = world * 8 * cp_bytes / (float(cms.item()) * 1e-3) / 1e9
+    e2e_h2d_gbs = e2e_fps * N_TX * 8 / 1e9
+    e2e["h2d_gb_per_s"] = e2e_h2d_gbs
+    e2e["pinned_h2d_ceiling_gb_per_s"] = agg_gbs
+    e2e["fraction_of_h2d_ceiling"] = e2e_h2d_gbs / agg_gbs
+    extra["pinned_h2d_ceiling"] = {"ranks": world, "aggregate_gb_per_s": agg_gbs, "rank0_gb_per_s": own_gbs, "bytes_per_copy": cp_bytes, "copies": 8,
+                                   "note": "all ranks copy 256 MiB of pinned host memory to their GPU at the same time, 8 times; aggregate = N x bytes / slowest rank"}
+    del h_big, d_big
+
+    # ---------------- single-process multi-GPU route (what a one-process host such as the Haskell tester uses) ----------------
+    # ldpc_b200_simulate_multi with n_gpus = N from rank 0 alone, after the timed regions, against the per-rank path's counters
+    if world > 1:
+        barrier()
+    sm_frames = 4096 * world
+    d_cnt.zero_()
+    torch.cuda.synchronize()
+    first, count = rank * 4096, 4096
+    dec.simulate_device(d_cnt.data_ptr(), MAX_ITERS, 3.5, code.K, N_TX, SEED, first, count)
+    dec.sync()
+    if world > 1:
+        dist.all_reduce(d_cnt)
+    per_rank_counters = [int(v) for v in d_cnt.cpu()]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=cpu_group)       # every GPU is idle from here until rank 0 is done driving all of them
+    if rank == 0:
+        try:
+            t0 = time.perf_counter()
+            got = lib.simulate_multi(dcode, world, "min", "fp32", 4096, MAX_ITERS, 3.5, code.K, N_TX, SEED, 0, sm_frames)
+            dt_sm = time.perf_counter() - t0
+            got_l = [int(got[k]) for k in ("frames", "frame_errors", "bit_errors", "sum_iters", "unconverged")]
+            extra["simulate_multi_single_process"] = {"n_gpus": world, "frames": sm_frames, "counters": got_l, "per_rank_path_counters": per_rank_counters,
+                                                      "identical": got_l == per_rank_counters, "first_call_s": dt_sm, "kernel_ms_max_over_gpus": got["kernel_ms"]}
+            assert got_l == per_rank_counters, (got_l, per_rank_counters)
+            lib.load().ldpc_b200_simulate_multi_release()
+        except lib.LdpcError as ex:
+            extra["simulate_multi_single_process"] = {"n_gpus": world, "error": str(ex)}
+    if world > 1:
+        dist.barrier(group=cpu_group)
+
+    # ---------------- extra operating points with early exit (reference semantics) ----------------
     if not args.no_extra:
         # float32 LLRs in / packed decisions out: half the PCIe bytes of the reference-typed call
         h32 = torch.empty((Be, code.N), dtype=torch.float32).pin_memory()
@@ -399,46 +479,77 @@ def main():
             for _ in range(200):
                 lib.check(L.ldpc_b200_ecc_decode(rec.h, 1, one_rx.data_ptr(), N_TX, one_out.data_ptr(), one_fl.data_ptr()))
             us = (time.perf_counter() - t0) / 200 * 1e6
-            extra["single_frame_call"] = {"api": "ldpc_b200_ecc_decode, n_frames = 1 (all 20 iterations run)", "us_per_call": us,
+            extra["single_frame_call"] = {"api": "ldpc_b200_ecc_decode, n_frames = 1 (all 20 iterations run), one caller: mailbox, latency kernel", "us_per_call": us,
                                           "frames_per_s": 1e6 / us, "info_gbit_per_s": code.K / us / 1e3}
+
+            # the tester's pattern at its own concurrency (Utils.hs:53: maxThreadCount decoders; B200.hs registers 16): T host
+            # threads, one ECC record each, one frame per ECC.decode call -- measured inside the library's C++ harness
+            # (ldpc_b200_ecc_tester_pattern), so no Python is in the loop; frames coalesce in the shared mailbox
+            name = "ldpc/b200-minsum/%s/%d/4/5" % (CODE, MAX_ITERS)
+            tp = {}
+            for label, ebn0 in (("worst_2.0dB_all_20_iterations", EBN0_WORST), ("4.0dB_early_exit", 4.0)):
+                gen(ebn0, 0)
+                nfp = 8192
+                rxp = d_llr[:nfp, :N_TX].double().cpu().numpy()
+                ref_bits = None
+                for T in (1, 4, 16, 32):
+                    nft = nfp if T >= 4 else 2048
+                    msg, secs, nl, nfr = lib.tester_pattern(codes.builtin_codes_dir(), name, T, rxp[:nft])
+                    if ref_bits is None:
+                        dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=True, d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
+                        dec.sync()
+                        ref_bits = lib.unpack_bits(d_bits[:nfp].cpu().numpy().view(np.uint32), code.N)[:, :code.K]
+                    tp["%s_threads_%d" % (label, T)] = {"threads": T, "frames": nft, "frames_per_s": nft / secs, "us_per_frame_per_thread": secs / (nft / T) * 1e6,
+                                                         "info_gbit_per_s": nft / secs * code.K / 1e9, "kernel_launches": nl,
+                                                         "frames_per_launch": (nfr / nl) if nl else None,
+                                                         "decisions_identical_to_batched_path": bool((msg == ref_bits[:nft]).all())}
+            tp["round1_single_caller_frames_per_s"] = 12500
+            extra["tester_pattern"] = tp
+            gen(EBN0_WORST, rank * B)
 
     # ---------------- CPU baseline beside it (rank 0, bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle
+        from ecc_ldpc_b200 import philox_host
         orc = oracle.Oracle(code)
         cores = oracle.lib().oracle_max_threads()
         gen(EBN0_WORST, 0)
         nf = args.cpu_frames or 64 * cores
         sample = d_llr[:nf].double().cpu().numpy()
-        gb = lib.unpack_bits(d_bits[:nf].cpu().numpy().view(np.uint32), code.N) if False else None
-        t0 = time.perf_counter()
-        rb, ri, rc = orc.decode_batch("min", MAX_ITERS, sample, variant=1, threads=cores)
-        dtc = time.perf_counter() - t0
+        # the host statement of the generator draws the same frames (the CPU arm of --impl reference relies on it)
+        host = philox_host.awgn_llrs(code.N, EBN0_WORST, code.K, N_TX, SEED, 0, 64)
+        gen_err = float(np.abs(host - sample[:64]).max() / np.abs(sample[:64]).max())
+        orc.decode_batch("min", MAX_ITERS, sample[: 4 * cores], variant=1, threads=cores)          # warm-up: threads, caches, page faults
+        reps = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rb, ri, rc = orc.decode_batch("min", MAX_ITERS, sample, variant=1, threads=cores)
+            reps.append(time.perf_counter() - t0)
+        dtc = float(np.median(reps))
         dec.decode_device(d_llr.data_ptr(), d_bits.data_ptr(), MAX_ITERS, B, early_exit=True, d_iters=d_iters.data_ptr(), d_conv=d_conv.data_ptr())
         dec.sync()
         gb = lib.unpack_bits(d_bits[:nf].cpu().numpy().view(np.uint32), code.N)
         same = float((gb == rb).all(axis=1).mean())
         cpu = {"value": nf / dtc * code.K / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d frames of the same LLRs (downloaded from the GPU), C restatement oracle/ldpc_oracle.c, two-minimum check update, %d threads, avg %.1f iterations" % (nf, cores, float(ri.mean())),
-               "frames_per_s": nf / dtc, "decisions_identical_to_gpu": same}
+               "sample": "%d frames of the same LLRs (downloaded from the GPU), C restatement oracle/ldpc_oracle.c, two-minimum check update, %d threads, avg %.1f iterations; median of 3 passes after a warm-up pass (%s s)" % (
+                   nf, cores, float(ri.mean()), ", ".join("%.3f" % r for r in reps)),
+               "frames_per_s": nf / dtc, "decisions_identical_to_gpu": same,
+               "host_generator_max_rel_diff_vs_device": gen_err}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s min-sum alpha=3/4, max %d iterations, rate 4/5 (n_tx=%d), all-zero codeword, BPSK+AWGN Eb/N0=%.1f dB (no frame converges: all %d iterations run)" % (CODE, MAX_ITERS, N_TX, EBN0_WORST, MAX_ITERS),
-                       "frames_per_step_per_gpu": B, "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident", 3: "onchip"}[dec.engine()],
-                       "l2": "inputs larger than L2 (%.0f MB of LLRs per step per GPU)" % (B * code.N * 4 / 1e6),
-                       "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step",
-                       "numa_node_rank0": numa},
+            "config": workload_config(B, code.N),
+            "avg_iters": avg_iters, "engine": {1: "stream", 2: "resident", 3: "onchip"}[dec.engine()], "numa_node_rank0": numa,
             "frames_per_s": fps, "edge_updates_per_s": fps * avg_iters * code.E,
             "gpu_launches": int(sum(launches) / len(launches) + 1) * args.steps,
             "clocks": clocks,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel_ms": k_ms, "alg_bytes_per_frame": b_alg,
+                         "traffic": traffic, "traffic_source": traffic_note, "kernel_ms": k_ms, "alg_bytes_per_frame": b_alg,
                          # the frame state is on chip, so beside the algorithmic figure report what HBM really
                          # carries (ncu dram bytes / live kernel time) and the resources that do bind (from the committed capture)
                          "measured_dram_gbs": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,

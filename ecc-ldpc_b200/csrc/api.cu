@@ -48,6 +48,24 @@ static std::set<ldpc_b200_code *> g_live_codes;
 template <class H> static void reg_add(std::set<H *> &s, H *h) { std::lock_guard<std::mutex> lk(g_reg_mu); s.insert(h); }
 template <class H> static bool reg_remove(std::set<H *> &s, H *h) { std::lock_guard<std::mutex> lk(g_reg_mu); return s.erase(h) != 0; }
 
+// One device copy of H per (device, content): mkLDPC calls `decoder0 h` maxThreadCount times (Utils.hs:53), i.e. a binding
+// creates the same code once per tester thread.  Sharing the object saves the copies and, more importantly, makes all those
+// decoder handles meet in ONE mailbox (mailbox.cu), which is what lets their one-frame calls coalesce.
+static std::mutex g_create_mu;
+static ldpc_b200_code *find_shared_code(int device, int M, int N, int sz, int brows, int bcols, const int32_t *shifts,
+                                        const int32_t *row_ptr, const int32_t *col_idx)
+{
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (ldpc_b200_code *c : g_live_codes) {
+        if (c->device != device || c->M != M || c->N != N || c->sz != sz || c->brows != brows || c->bcols != bcols) continue;
+        const bool same = sz > 0 ? std::equal(c->shifts.begin(), c->shifts.end(), shifts)
+                                 : (std::equal(c->row_ptr.begin(), c->row_ptr.end(), row_ptr) &&
+                                    std::equal(c->col_idx.begin(), c->col_idx.begin() + c->row_ptr[M], col_idx));
+        if (same) { c->refs++; return c; }
+    }
+    return nullptr;
+}
+
 static int require_init()
 {
     if (!g_init) {
@@ -295,7 +313,7 @@ void ldpc_b200_shutdown(void)
     }
     for (;;) {
         ldpc_b200_code *c = nullptr;
-        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_codes.empty()) c = *g_live_codes.begin(); }
+        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_codes.empty()) { c = *g_live_codes.begin(); c->refs = 1; } }
         if (!c) break;
         ldpc_b200_code_destroy(c);
     }
@@ -305,7 +323,7 @@ void ldpc_b200_shutdown(void)
 int ldpc_b200_live_handles(int *codes, int *decoders)
 {
     std::lock_guard<std::mutex> lk(g_reg_mu);
-    if (codes) *codes = (int)g_live_codes.size();
+    if (codes) { *codes = 0; for (const ldpc_b200_code *c : g_live_codes) *codes += c->refs; }      // handles, not objects
     if (decoders) *decoders = (int)g_live_decs.size();
     return 0;
 }
@@ -323,6 +341,12 @@ int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_
     }
     int rc = require_init();
     if (rc) return rc;
+    std::lock_guard<std::mutex> create_lock(g_create_mu);
+    {
+        int dev = -1;
+        LDPC_CUDA(cudaGetDevice(&dev));
+        if (ldpc_b200_code *shared = find_shared_code(dev, M, N, 0, 0, 0, nullptr, row_ptr, col_idx)) { *out = shared; return 0; }
+    }
     ldpc_b200_code *c = new (std::nothrow) ldpc_b200_code();
     if (!c) return LDPC_B200_ENOMEM;
     c->M = M; c->N = N;
@@ -348,6 +372,12 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
         if (shifts[i] < -1 || shifts[i] >= sz) { set_error("code_create_qc: shift %d out of range [-1, %d)", shifts[i], sz); return LDPC_B200_EINVAL; }
     int rc = require_init();
     if (rc) return rc;
+    std::lock_guard<std::mutex> create_lock(g_create_mu);
+    {
+        int dev = -1;
+        LDPC_CUDA(cudaGetDevice(&dev));
+        if (ldpc_b200_code *shared = find_shared_code(dev, brows * sz, bcols * sz, sz, brows, bcols, shifts, nullptr, nullptr)) { *out = shared; return 0; }
+    }
     ldpc_b200_code *c = new (std::nothrow) ldpc_b200_code();
     if (!c) return LDPC_B200_ENOMEM;
     c->M = brows * sz; c->N = bcols * sz;
@@ -380,7 +410,14 @@ int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts
 
 void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
 {
-    if (!c || !reg_remove(g_live_codes, c)) return;
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        auto it = g_live_codes.find(c);
+        if (it == g_live_codes.end()) return;              // already released (e.g. by ldpc_b200_shutdown)
+        if (--c->refs > 0) return;                          // other handles still share it
+        g_live_codes.erase(it);
+    }
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
     cudaFree(c->g.row_ell); cudaFree(c->g.col_ell); cudaFree(c->g.oc_tab); cudaFree(c->g.oc_posvar); cudaFree(c->g.col_slot);
     delete c;

@@ -52,6 +52,7 @@ struct ldpc_b200_code {
     int sz = 0, brows = 0, bcols = 0;
     std::vector<int32_t> shifts;
     int device = -1;
+    int refs = 1;                 // handles sharing this object: creating an identical code on the same device returns it again
     ldpc::DeviceGraph g;          // device copy
     int resident_kind = 0;        // 0 = none, 1 / 2 = compiled RESIDENT specialisation, 3 = run-time table ONCHIP kernel
     // ONCHIP placement, host copy (message tap: slot of reference edge e, position of variable j)

@@ -9,6 +9,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -606,4 +609,59 @@ extern "C" int ldpc_b200_ber_line(char *buf, int buf_len, double seconds, const 
     }
     return snprintf(buf, buf_len, "%.2f %s %.1f %llu %llu %s +%.0f%% -%.0f%% 95%%", seconds, name ? name : "", ebn0_db,
                     (unsigned long long)frames, (unsigned long long)bit_errors, ber, up, dn);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The tester's calling pattern (Utils.hs:53,62-69): maxThreadCount decoders, one frame per decode call, concurrent callers
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int ldpc_b200_ecc_tester_pattern(const char *codes_root, const char *name, int n_threads, int n_frames, const double *rx,
+                                            int rx_len, uint8_t *out, double *seconds, uint64_t *mailbox_launches, uint64_t *mailbox_frames)
+{
+    if (!codes_root || !name || n_threads <= 0 || n_threads > 256 || n_frames < 0 || (n_frames && (!rx || !out)) || rx_len <= 0) {
+        set_error("ecc_tester_pattern: bad arguments");
+        return LDPC_B200_EINVAL;
+    }
+    std::vector<ldpc_b200_ecc_t *> recs(n_threads, nullptr);
+    int rc = 0;
+    for (int t = 0; t < n_threads && !rc; t++) rc = ldpc_b200_ecc_open(codes_root, name, 1, &recs[t]);
+    const int K = rc ? 0 : recs[0]->K;
+    // warm-up outside the clock: device copies of H, the mailbox, the kernels' first launch
+    std::vector<uint8_t> scratch(K > 0 ? K : 1);
+    for (int t = 0; t < n_threads && !rc && n_frames > 0; t++) rc = ldpc_b200_ecc_decode(recs[t], 1, rx, rx_len, scratch.data(), nullptr);
+    uint64_t l0 = 0, f0 = 0;
+    if (!rc && recs[0]->dec) ldpc_b200_decoder_mailbox_stats(recs[0]->dec, &l0, &f0);
+    std::vector<int> rcs(n_threads, 0);
+    std::vector<std::string> errs(n_threads);
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    auto worker = [&](int t) {
+        ready.fetch_add(1);
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        for (int f = t; f < n_frames; f += n_threads) {
+            int r = ldpc_b200_ecc_decode(recs[t], 1, rx + (size_t)f * rx_len, rx_len, out + (size_t)f * K, nullptr);
+            if (r) { rcs[t] = r; errs[t] = ldpc_b200_last_error(); return; }
+        }
+    };
+    double secs = 0.0;
+    if (!rc) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(worker, t);
+        while (ready.load() < n_threads) std::this_thread::yield();
+        const auto t0 = std::chrono::steady_clock::now();
+        go.store(true, std::memory_order_release);
+        for (auto &x : th) x.join();
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int t = 0; t < n_threads; t++) if (rcs[t]) { set_error("ecc_tester_pattern: thread %d: %s", t, errs[t].c_str()); rc = rcs[t]; break; }
+    }
+    if (!rc) {
+        uint64_t l1 = 0, f1 = 0;
+        if (recs[0]->dec) ldpc_b200_decoder_mailbox_stats(recs[0]->dec, &l1, &f1);
+        if (mailbox_launches) *mailbox_launches = l1 - l0;
+        if (mailbox_frames) *mailbox_frames = f1 - f0;
+        if (seconds) *seconds = secs;
+    }
+    std::string keep = rc ? ldpc_b200_last_error() : "";
+    for (auto *e : recs) if (e) ldpc_b200_ecc_close(e);
+    if (rc) set_error("%s", keep.c_str());
+    return rc;
 }

@@ -40,6 +40,7 @@ ECC_EXPORTS = [
     "ldpc_b200_ecc_name", "ldpc_b200_ecc_message_length", "ldpc_b200_ecc_codeword_length",
     "ldpc_b200_ecc_unpunctured_length", "ldpc_b200_ecc_max_iters", "ldpc_b200_ecc_encode", "ldpc_b200_ecc_decode",
     "ldpc_b200_ecc_run", "ldpc_b200_ber_line", "ldpc_b200_ecc_encode_device", "ldpc_b200_ecc_sync",
+    "ldpc_b200_ecc_tester_pattern",
 ]
 ENOMATCH, ENOENT = -6, -7
 
@@ -130,6 +131,7 @@ def load():
     L.ldpc_b200_ber_line.argtypes = [cs, i32, f64, cs, f64, u64, u64, i32]
     L.ldpc_b200_ecc_encode_device.argtypes = [vp, i32, vp, vp]
     L.ldpc_b200_ecc_sync.argtypes = [vp]
+    L.ldpc_b200_ecc_tester_pattern.argtypes = [cs, cs, i32, i32, vp, i32, vp, C.POINTER(f64), C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -452,6 +454,22 @@ class Ecc:
             self.close()
         except Exception:
             pass
+
+
+def tester_pattern(codes_root, name, n_threads, rx):
+    """ldpc_b200_ecc_tester_pattern: n_threads tester threads, one ECC.decode call per frame.  Returns (message bits
+    [F, K], seconds, mailbox launches, mailbox frames)."""
+    rx = np.ascontiguousarray(rx, dtype=np.float64)
+    F, rl = rx.shape
+    e = Ecc(codes_root, name, 1)
+    K = e.message_length
+    e.close()
+    out = np.zeros((F, K), dtype=np.uint8)
+    secs = C.c_double(0)
+    nl, nf = C.c_uint64(0), C.c_uint64(0)
+    check(load().ldpc_b200_ecc_tester_pattern(codes_root.encode(), name.encode(), n_threads, F, rx.ctypes.data, rl, out.ctypes.data,
+                                              C.byref(secs), C.byref(nl), C.byref(nf)))
+    return out, secs.value, nl.value, nf.value
 
 
 def ber_line(seconds, name, ebn0_db, frames, bit_errors, message_length):

@@ -78,6 +78,15 @@ int ldpc_b200_ecc_run(ldpc_b200_ecc_t *e, double ebn0_db, uint64_t seed, uint64_
 int ldpc_b200_ber_line(char *buf, int buf_len, double seconds, const char *name, double ebn0_db,
                        uint64_t frames, uint64_t bit_errors, int message_length);
 
+/* The reference tester's calling pattern as a measurable unit (Utils.hs:53,62-69): `n_threads` tester threads,
+ * thread t owning decoder t (one ECC record each, opened like mkLDPC's `replicateM maxThreadCount (decoder0 h)`), every thread
+ * calling ECC.decode with ONE received vector per call for its share of the frames (frame f belongs to thread f mod
+ * n_threads).  rx: n_frames x rx_len; out: n_frames x message_length.  *seconds = wall time from the common start of the
+ * threads to the last join (records are opened and warmed before the clock starts).  mailbox_launches / mailbox_frames
+ * (may be NULL): how many kernel launches served the calls. */
+int ldpc_b200_ecc_tester_pattern(const char *codes_root, const char *name, int n_threads, int n_frames, const double *rx, int rx_len,
+                                 uint8_t *out, double *seconds, uint64_t *mailbox_launches, uint64_t *mailbox_frames);
+
 /* Device encoder on packed words: d_msg n_frames x ceil(K/32) -> d_cw n_frames x ceil(N/32) with the
  * parity bits beyond codeword_length cleared. Asynchronous on the ECC's decoder stream. */
 int ldpc_b200_ecc_encode_device(ldpc_b200_ecc_t *e, int n_frames, const uint32_t *d_msg_packed, uint32_t *d_cw_packed);
