@@ -60,6 +60,67 @@ __device__ __forceinline__ uint32_t rot(uint32_t P)
 
 template <typename T> __device__ __forceinline__ T minus34() { return (T)-0.75; }
 
+// Duplicated posterior columns (RES_DUP): every block column of mu is stored TWICE back to back (2*SZ entries, entry x
+// holding variable x mod SZ), so the rotated read of variable (i + s) mod SZ by the thread of check position i is the plain
+// address [P + c*2*BLK + s*sizeof(T)] -- an immediate, no add and no bit-select -- for all 99 non-zero-shift circulants in
+// the check phase (and the syndrome pass).  The price: the LAST link of a column's chain, which finishes the posterior,
+// stores it to both halves (one extra STS per column and iteration; intermediate partial sums live in the first half
+// only), and 22 KB more shared memory per float32 frame of jpl.4096.4.5 (90 KB per CTA: still two CTAs per SM).
+// MEASURED AND REJECTED (round 2, B200, jpl.4096.4.5 min-sum, 20 iterations): static instructions 4768 -> 4280, but
+// 21.6 Gbit/s with it against 22.4 without (with the fused normalisation: 22.6 against 23.1) -- the kernel is bound by
+// shared-memory wavefronts as much as by issue slots (2.7 accesses per edge and iteration: 66 % of the LSU roof), and the
+// 44 extra stores per iteration cost more than the 200 saved integer instructions.  Kept as a build switch.
+#ifndef RES_DUP
+#define RES_DUP 0
+#endif
+template <class C, typename T> struct Lay {
+    static constexpr int BLK = C::SZ * (int)sizeof(T);            // one block column, bytes
+    static constexpr int CB = RES_DUP ? 2 * BLK : BLK;            // column stride of mu, bytes
+    static constexpr int N = C::BC * C::SZ;
+    static constexpr int MUE = RES_DUP ? 2 * N : N;               // elements of mu per frame
+    static constexpr int NEGL = MUE * (int)sizeof(T);             // byte offset of negL behind mu (block columns of BLK bytes)
+    static constexpr int FS = MUE + N;                            // elements of mu + negL per frame
+    static __host__ __device__ constexpr int mu_index(int j) { return RES_DUP ? j + (j & ~(C::SZ - 1)) : j; }   // variable j in mu
+    // mu of variable (c, (i + S) mod SZ) for the thread whose P = address of mu entry (0, i)
+    template <int c, int S> static __device__ __forceinline__ T lds_mu(uint32_t P)
+    {
+        if constexpr (RES_DUP) return FB<T>::template lds<c * CB + S * (int)sizeof(T)>(P);
+        else return FB<T>::template lds<c * BLK>(rot<C, T, S>(P));
+    }
+};
+
+// Fused normalisation (float32 min-sum): the message registers hold the UNSCALED leave-one-out reduction r, the reference's
+// message being ne' = -3/4 r (Min.hs:79); its two consumers take the factor into a fused multiply-add --
+//     x   = ne' + mu   = fma(-3/4, r, mu)        (check phase, Min.hs:80)
+//     mu' = acc - ne'  = fma(+3/4, r, acc)       (variable phase, Orig.hs:95-98)
+// -- so the multiply costs no instruction of its own (one of 12.3 per edge and iteration) and the product is not rounded
+// separately (one rounding instead of two: closer to the float64 reference, no longer bit-identical to "multiply, then
+// add").  The float64 instances keep the reference's separate multiply: they reproduce its arithmetic bit for bit.
+#ifndef RES_FUSE_SCALE
+#define RES_FUSE_SCALE 1
+#endif
+template <typename T, int ALGO> struct MsgForm {
+    static constexpr bool FUSED = RES_FUSE_SCALE && sizeof(T) == 4 && ALGO == LDPC_B200_ALGO_MINSUM;
+    // x of the next check phase from the stored message s and the (negated) posterior
+    static __device__ __forceinline__ T x_of(T s, T mu)
+    {
+        if constexpr (FUSED) return __fmaf_rn(-0.75f, s, mu); else return FB<T>::add(s, mu);
+    }
+    // one link of the posterior chain: acc - ne'
+    static __device__ __forceinline__ T link(T acc, T s)
+    {
+        if constexpr (FUSED) return __fmaf_rn(0.75f, s, acc); else return FB<T>::sub(acc, s);
+    }
+    static __device__ __forceinline__ T store(T others)            // what the check phase leaves in the register
+    {
+        if constexpr (FUSED) return others; else return FB<T>::mul(minus34<T>(), others);
+    }
+    static __device__ __forceinline__ T value(T s)                 // the reference's ne' (message tap)
+    {
+        if constexpr (FUSED) return __fmul_rn(-0.75f, s); else return s;
+    }
+};
+
 // Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
 // round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
 // zero (punctured LLR, or a sum that cancels) is +0.0 in mu, and mu is never -0.0 (x + y = -0 needs both operands
@@ -88,9 +149,9 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
             if constexpr (!(FOLD && QcMap<C>::is_final_edge(r, k))) {
-                T m = F::template lds<c * BLK>(rot<C, T, s>(P));
+                T m = Lay<C, T>::template lds_mu<c, s>(P);
                 par ^= F::bits(m);
-                ne[base + k] = F::add(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
+                ne[base + k] = MsgForm<T, ALGO>::x_of(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
             }
         });
         unsat |= par;
@@ -98,7 +159,7 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
             // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
             BoxTree<T, 0, d> tree;
             tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
-            tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = F::mul(minus34<T>(), others); });
+            tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = MsgForm<T, ALGO>::store(others); });
         } else if constexpr (sizeof(T) == 4) {
             // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form
             uint32_t sgn = 0;
@@ -174,7 +235,7 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
                 uint32_t par = 0, sgn = 0;
                 static_for<d>([&](auto ki) {
                     constexpr int k = decltype(ki)::value;
-                    float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                    float m = Lay<C, float>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P);
                     par ^= F::bits(m);
                     ne[base + k] = F::add(ne[base + k], m);
                     sgn ^= F::bits(ne[base + k]);
@@ -201,7 +262,7 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
             constexpr int base = QcMap<C>::reg_base(r);
             static_for<D>([&](auto ki) {
                 constexpr int k = decltype(ki)::value;
-                float m = F::template lds<C::row_col[r][k] * BLK>(rot<C, float, C::row_shift[r][k]>(P));
+                float m = Lay<C, float>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P);
                 par ^= F::bits(m);
                 xs[k] = F::add(ne[base + k], m);                  // x = ne + mu   (Orig.hs:84)
             });
@@ -247,7 +308,7 @@ __device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
         typename F::B par = 0;
         static_for<d>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
-            par ^= F::bits(F::template lds<C::row_col[r][k] * BLK>(rot<C, T, C::row_shift[r][k]>(P)));
+            par ^= F::bits(Lay<C, T>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P));
         });
         unsat |= par;
     });
@@ -256,13 +317,12 @@ __device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
 
 // Variable-node stage Q for part H.  Column c builds mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the
 // exact negation of Orig.hs:95-98, one link per stage from the innermost (last block row) outwards; col_stage
-// says which link runs in which stage.  negL sits N*sizeof(T) bytes after mu.
-template <class C, typename T, int H, int Q, bool FOLD>
+// says which link runs in which stage.  negL sits Lay::NEGL bytes after mu.
+template <class C, typename T, int H, int Q, bool FOLD, int ALGO>
 __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
 {
     typedef FB<T> F;
-    constexpr int BLK = C::SZ * sizeof(T);
-    constexpr int NEGL = QcMap<C>::N * sizeof(T);
+    constexpr int BLK = Lay<C, T>::BLK, CB = Lay<C, T>::CB, NEGL = Lay<C, T>::NEGL;
     // Two passes: every load of the stage is issued before the first store.  The accesses are volatile asm and keep
     // their program order, so a fused load-subtract-store per link would serialise the stage on shared-memory latency.
     T acc[C::BC];
@@ -274,7 +334,7 @@ __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>:
             if constexpr (C::half_of_row[r] == H) {
                 constexpr int k = C::col_k_desc[c][step];
                 uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                acc[c] = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * BLK>(a);
+                acc[c] = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * CB>(a);
             }
         }
     });
@@ -287,11 +347,12 @@ __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>:
                 constexpr int k = C::col_k_desc[c][step];
                 constexpr int e = QcMap<C>::reg_base(r) + k;
                 uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                const T val = F::sub(acc[c], ne[e]);
-                F::template sts<c * BLK>(a, val);
+                const T val = MsgForm<T, ALGO>::link(acc[c], ne[e]);
+                F::template sts<c * CB>(a, val);
+                if constexpr (RES_DUP && step == C::col_deg[c] - 1) F::template sts<c * CB + BLK>(a, val);      // the finished posterior: both halves
                 if constexpr (FOLD && step == C::col_deg[c] - 1) {
                     // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
-                    ne[e] = F::add(ne[e], val);                                  // x of the next check phase
+                    ne[e] = MsgForm<T, ALGO>::x_of(ne[e], val);                  // x of the next check phase
                     fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
                 }
             }
@@ -338,7 +399,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             static_for<C::row_deg[r]>([&](auto ki) {
                 constexpr int k = decltype(ki)::value;
                 if constexpr (Mp::is_final_edge(r, k)) {
-                    T m = FB<T>::template lds<C::row_col[r][k] * C::SZ * (int)sizeof(T)>(rot<C, T, C::row_shift[r][k]>(P));
+                    T m = Lay<C, T>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P);
                     ne[Mp::reg_base(r) + k] = m;
                     fpar[decltype(qi)::value] ^= FB<T>::bits(m);
                 }
@@ -365,12 +426,13 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
         if (finished_now) {
             // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
             done = true;
-            const T *src = conv ? mu : negL;
             const unsigned int fi = p.use_map ? p.slot_map[f] : f;
-            uint32_t *obuf = reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC * 2 - 2 * (bar - 1) - 1) * N + (size_t)(bar - 1) * N);
+            // the staging row of this slot (see k_resident): stage - negL = (FPC - slot) * FS - MUE + slot * N
+            uint32_t *obuf = reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC - (bar - 1)) * Lay<C, T>::FS - Lay<C, T>::MUE + (size_t)(bar - 1) * N);
             unsigned int errs = 0;
             for (int w = wif; w < W; w += WPF) {
-                unsigned int word = __ballot_sync(0xffffffffu, src[32 * w + lane] < (T)0);   // lam > 0 <=> -lam < 0
+                const int j = 32 * w + lane;
+                unsigned int word = __ballot_sync(0xffffffffu, (conv ? mu[Lay<C, T>::mu_index(j)] : negL[j]) < (T)0);   // lam > 0 <=> -lam < 0
                 if (lane == 0) {
                     if (p.done) obuf[w] = word;
                     else if (p.bits) p.bits[(size_t)fi * W + w] = word;
@@ -413,7 +475,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
                     static_for<C::HR>([&](auto qi) {
                         constexpr int r = C::half_rows[HH][decltype(qi)::value];
                         constexpr int d = C::row_deg[r];
-                        static_for<d>([&](auto ki) { out[RefEdge<C>::row_base(r) + i * d + decltype(ki)::value] = ne[Mp::reg_base(r) + decltype(ki)::value]; });
+                        static_for<d>([&](auto ki) { out[RefEdge<C>::row_base(r) + i * d + decltype(ki)::value] = MsgForm<T, ALGO>::value(ne[Mp::reg_base(r) + decltype(ki)::value]); });
                     });
                 });
             }
@@ -421,15 +483,15 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
 
         // ---- variable phase ----
         static_for<C::MAXCD>([&](auto qi) {
-            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value, FOLD>(ne, fpar, P);
-            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value, false>(ne, fpar, P); });
+            if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value, FOLD, ALGO>(ne, fpar, P);
+            else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value, false, ALGO>(ne, fpar, P); });
             bar_sync(bar, TPF);
         });
 
         if constexpr (TRACE) {
             if (f == 0 && p.trace_lam) {        // lam' = -mu (Orig.hs:95-98); every stage ended behind a barrier
                 T *out = reinterpret_cast<T *>(p.trace_lam) + (size_t)n * N;
-                for (int j = tf; j < N; j += TPF) out[j] = -mu[j];
+                for (int j = tf; j < N; j += TPF) out[j] = -mu[Lay<C, T>::mu_index(j)];
             }
         }
     }
@@ -447,14 +509,19 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
     const int slot = threadIdx.x / TPF, tf = threadIdx.x % TPF;
     const int h = tf / SZ, i = tf % SZ, lane = threadIdx.x & 31;
     const int bar = slot + 1;
-    T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * 2 * N;      // negated posterior, see above
-    T *negL = mu + N;                                                    // negated channel LLRs
+    constexpr int FS = Lay<C, T>::FS, MUE = Lay<C, T>::MUE;
+    T *mu = reinterpret_cast<T *>(smem_raw) + (size_t)slot * FS;         // negated posterior, see above (columns duplicated: Lay)
+    T *negL = mu + MUE;                                                  // negated channel LLRs
     // staging row of the NEXT frame's LLRs (host-supplied frames only): fetched by one bulk copy while this frame decodes;
     // in mailbox mode (no prefetch) the same row stages the packed decisions
-    T *stage = reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 2 * N + (size_t)slot * N;
-    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * 3 * N);
+    T *stage = reinterpret_cast<T *>(smem_raw) + (size_t)FPC * FS + (size_t)slot * N;
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * (FS + N));
     uint64_t *mbar = reinterpret_cast<uint64_t *>(s_next + ((FPC + 1) & ~1)) + slot;
     const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
+    auto put_mu = [&](int j, T v) {                       // initial posterior of variable j (both halves of a duplicated column)
+        mu[Lay<C, T>::mu_index(j)] = v;
+        if constexpr (RES_DUP) mu[Lay<C, T>::mu_index(j) + SZ] = v;
+    };
     const bool prefetch = p.llr != nullptr && p.llr_bulk && p.work != nullptr;
     constexpr uint32_t ROWB = N * sizeof(T);
 
@@ -489,7 +556,7 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
         if (prefetch) {
             mbar_wait(mbar, phase);
             phase ^= 1u;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, stage[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, stage[j]); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
             bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
             if (tf == 0) {
                 const unsigned int nxt = atomicAdd(p.work, 1u);
@@ -498,12 +565,12 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
             }
         } else if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)fi * N;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; mu[j] = v; }   // 0 - L: never -0.0
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
             bar_sync(bar, TPF);
         } else if (p.llr64) {
             // the reference's float64 vector, rounded to T exactly as the host-side conversion would; unpuncture (Utils.hs:55)
             const double *src = p.llr64 + (size_t)fi * p.llr64_stride;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, j < p.llr64_take ? (T)src[j] : (T)0); negL[j] = v; mu[j] = v; }
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, j < p.llr64_take ? (T)src[j] : (T)0); negL[j] = v; put_mu(j, v); }
             bar_sync(bar, TPF);
         } else {
             for (int g = tf; g < N / 4; g += TPF) {
@@ -513,7 +580,7 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
                 for (int q = 0; q < 4; q++) {
                     int j = 4 * g + q;
                     T v = F::sub((T)0, (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0);
-                    negL[j] = v; mu[j] = v;
+                    negL[j] = v; put_mu(j, v);
                 }
             }
             bar_sync(bar, TPF);
@@ -552,7 +619,7 @@ static int launch_instance(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t
 {
     typedef QcMap<C> Mp;
     auto kern = k_resident<C, T, FPC, ALGO, MINB, TRACE>;
-    size_t smem = (size_t)FPC * 3 * Mp::N * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
+    size_t smem = (size_t)FPC * (Lay<C, T>::FS + Mp::N) * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
     static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
     static std::atomic<int> cfg_bps[MAX_DEVICES], cfg_sm[MAX_DEVICES];
     const int dev = d->code->device;
