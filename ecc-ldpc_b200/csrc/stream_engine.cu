@@ -29,6 +29,8 @@ namespace ldpc {
 #define STREAM_TPB 128
 #endif
 static constexpr int TPB = STREAM_TPB;   // threads per block along the frame axis
+static constexpr int ACTIVE_SLOTS = 1024; // per-iteration "frames still running" counters (iteration n uses slot n mod ACTIVE_SLOTS)
+static constexpr int SYNC_EVERY = 4;      // the host looks at the counter every SYNC_EVERY iterations (see stream_decode_t)
 
 // The messages are stored frame-block-major, ne[frame block][E][TPB]: the d message rows of a check for one block of
 // frames are then ONE contiguous chunk (one bulk copy in, one out, instead of d each way; the kernels are bound by the
@@ -110,25 +112,32 @@ __global__ void k_status(uint8_t *__restrict__ state, uint8_t *__restrict__ unsa
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(active, __popc(b));
 }
 
-// Hard decision of the frames that stopped at iteration n: lam if converged, L on fallback.
-// Thread = (32-bit word, frame); reads are coalesced over frames.
+// Hard decision of the frames that stopped at iteration n: lam if converged, L on fallback.  It has to run in the iteration
+// the frame stops: the staged kernels below move whole 128-frame rows, so a stopped frame's posteriors are overwritten by
+// later launches.  CTA = (HARD_WPC words, 128 frames); most launches find no frame that stopped and leave at once, which is
+// why a CTA covers several words (11 440 one-word CTAs per launch cost ~10 us of pure scheduling).
+static constexpr int HARD_WPC = 8;
 template <typename T>
 __global__ void k_hard(const T *__restrict__ lam, const T *__restrict__ L, const uint8_t *__restrict__ state,
                        const int32_t *__restrict__ iters, uint32_t *__restrict__ bits, int n, int N, int F, int Bp)
 {
-    int f = blockIdx.y * TPB + threadIdx.x, w = blockIdx.x;
-    if (f >= F) return;
-    uint8_t s = state[f];
-    if (s == 0 || iters[f] != n) return;
+    const int f = blockIdx.y * TPB + threadIdx.x;
+    const uint8_t s = f < F ? state[f] : 0;
+    const bool mine = s != 0 && iters[f] == n;
+    if (!__syncthreads_or(mine)) return;
+    if (!mine) return;
     const T *src = (s == 1) ? lam : L;
-    uint32_t word = 0;
-    int j0 = w * 32;
+    const int W = (N + 31) / 32;
+    for (int w = blockIdx.x * HARD_WPC; w < min(W, (int)(blockIdx.x + 1) * HARD_WPC); w++) {
+        uint32_t word = 0;
+        const int j0 = w * 32;
 #pragma unroll 8
-    for (int b = 0; b < 32; b++) {
-        int j = j0 + b;
-        if (j < N && src[(size_t)j * Bp + f] > (T)0) word |= (1u << b);
+        for (int b = 0; b < 32; b++) {
+            const int j = j0 + b;
+            if (j < N && src[(size_t)j * Bp + f] > (T)0) word |= (1u << b);
+        }
+        bits[(size_t)f * W + w] = word;
     }
-    bits[(size_t)f * ((N + 31) / 32) + w] = word;
 }
 
 // Utils.hs:113-117
@@ -435,7 +444,7 @@ static int stream_alloc_buffers(ldpc_b200_decoder *d)
     LDPC_CUDA(cudaMalloc(&s.iters, sizeof(int32_t) * Bp));
     LDPC_CUDA(cudaMalloc(&s.state, Bp));
     LDPC_CUDA(cudaMalloc(&s.unsat, Bp));
-    LDPC_CUDA(cudaMalloc(&s.active, sizeof(int)));
+    LDPC_CUDA(cudaMalloc(&s.active, sizeof(int) * ACTIVE_SLOTS));        // one counter per iteration (zeroed once per decode)
     return 0;
 }
 
@@ -525,6 +534,7 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
     LDPC_CUDA(cudaMemsetAsync(s.state, 0, Bp, st));
     LDPC_CUDA(cudaMemsetAsync(s.unsat, 0, Bp, st));
     LDPC_CUDA(cudaMemsetAsync(s.iters, 0, sizeof(int32_t) * Bp, st));
+    LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int) * ACTIVE_SLOTS, st));
     {
         dim3 grid((N + 31) / 32, (Bp + 31) / 32), blk(32, 8);
         if (llr_is_double) k_load<T, double><<<grid, blk, 0, st>>>((const double *)d_llr, (T *)s.L, (T *)s.lam, N, F, Bp);
@@ -551,14 +561,19 @@ static int stream_decode_t(ldpc_b200_decoder *d, int max_iters, int early_exit, 
                                                                                    : launch_cn<T, LDPC_B200_ALGO_MINSUM>(d, fb, F, skip);
             if (rc) return rc;
         }
-        LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int), st));
-        k_status<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.unsat, s.iters, s.active, n, max_iters, F);
-        k_hard<T><<<dim3(words_per_frame(N), fb), TPB, 0, st>>>((const T *)s.lam, (const T *)s.L, s.state, s.iters, d_bits, n, N, F, Bp);
-        d->launches += 2;
+        // frames still running after the test of iteration n are counted in slot n of `active` (all slots zeroed above)
+        if (n > 0 && n % ACTIVE_SLOTS == 0) LDPC_CUDA(cudaMemsetAsync(s.active, 0, sizeof(int) * ACTIVE_SLOTS, st));
+        k_status<<<(F + 255) / 256, 256, 0, st>>>(s.state, s.unsat, s.iters, s.active + n % ACTIVE_SLOTS, n, max_iters, F);
+        d->launches++;
+        k_hard<T><<<dim3((words_per_frame(N) + HARD_WPC - 1) / HARD_WPC, fb), TPB, 0, st>>>((const T *)s.lam, (const T *)s.L, s.state, s.iters, d_bits, n, N, F, Bp);
+        d->launches++;
         if (n >= max_iters) break;
-        if (early_exit) {
+        // "Has every frame stopped?" costs a device -> host copy and a stream synchronisation, during which the GPU idles: asked
+        // only every SYNC_EVERY iterations (and while tracing); the launches issued past the last active iteration find all their
+        // frames idle and exit at once.
+        if (early_exit && (n % SYNC_EVERY == SYNC_EVERY - 1 || n == 0 || h_c2v || h_lam)) {
             int active = 0;
-            LDPC_CUDA(cudaMemcpyAsync(&active, s.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LDPC_CUDA(cudaMemcpyAsync(&active, s.active + n % ACTIVE_SLOTS, sizeof(int), cudaMemcpyDeviceToHost, st));
             LDPC_CUDA(cudaStreamSynchronize(st));
             if (active == 0) break;
         }
