@@ -131,15 +131,18 @@ void mailbox_release(ldpc_b200_decoder *d)
     }
 }
 
-static int acquire_slot(Mailbox *m)
+// n slots at once, all or nothing (one compare-and-swap): a caller never holds some slots while it waits for others, so
+// callers with several frames each cannot deadlock on a full arena.
+static void acquire_slots(Mailbox *m, int n, int *slots)
 {
     for (int spin = 0;; spin++) {
         uint64_t mask = m->free_mask.load(std::memory_order_acquire);
-        while (mask) {
-            int s = __builtin_ctzll(mask);
-            if (m->free_mask.compare_exchange_weak(mask, mask & ~(1ull << s), std::memory_order_acq_rel)) return s;
+        while (__builtin_popcountll(mask) >= n) {
+            uint64_t take = 0, rest = mask;
+            for (int k = 0; k < n; k++) { const int s = __builtin_ctzll(rest); slots[k] = s; take |= 1ull << s; rest &= rest - 1; }
+            if (m->free_mask.compare_exchange_weak(mask, mask & ~take, std::memory_order_acq_rel)) return;
         }
-        if (spin < 64) _mm_pause(); else std::this_thread::yield();       // all slots in flight: more callers than slots
+        if (spin < 64) _mm_pause(); else std::this_thread::yield();       // arena in flight: more frames than slots
     }
 }
 
@@ -202,9 +205,10 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
     if (out_take <= 0 || out_take > N) out_take = N;
     int slots[MB_SLOTS];
     if (n_frames > MB_SLOTS / 4) { set_error("mailbox_decode: batch of %d frames belongs on the batched path", n_frames); return LDPC_B200_EINVAL; }
+    acquire_slots(m, n_frames, slots);
     m->preparing.fetch_add(1, std::memory_order_acq_rel);
     for (int f = 0; f < n_frames; f++) {
-        const int s = slots[f] = acquire_slot(m);
+        const int s = slots[f];
         memcpy(m->h_llr + (size_t)s * N, llr + (size_t)f * stride, (size_t)take * sizeof(double));
         __atomic_store_n(&m->h_done[s], 0u, __ATOMIC_RELAXED);
     }

@@ -76,7 +76,7 @@ for name, algo, iters, n_tx, grid, gframes in CONFIGS:
         gf = c["frame_errors"] / c["frames"]
         print("| %.2f | %d | %.3e [%.2e, %.2e] | %.3e | %.2f | %d / %d | %d / %d | %d | %.5f | %.3e [%.2e, %.2e] | %s |" % (
             eb, c["frames"], gf, glo, ghi, c["bit_errors"] / (c["frames"] * code.K), c["sum_iters"] / c["frames"],
-            gfe, cfe, gbe, cbe, diff, eqit / C, cfe / C, clo, chi, "yes" if clo <= gf <= chi else "NO"))
+            gfe, cfe, gbe, cbe, diff, eqit / C, cfe / C, clo, chi, "yes" if (clo - 1e-12 <= gf <= chi + 1e-12) else "NO"))
         sys.stdout.flush()
     print()
     buf.free(); dec.close(); dc.close()
