@@ -1023,3 +1023,35 @@ def test_tester_pattern_harness(gpu_lib, builtin_codes, oracles):
     mm, sm, lm, fm = gpu_lib.tester_pattern(codes.builtin_codes_dir(), "ldpc/b200-spa/moon.7.13/20", 8, rxm)
     rb, ri, rc = oracles["moon.7.13"].decode_batch("spa", 20, rxm)
     assert (mm == rb[:, :moon.K]).all(axis=1).mean() >= 0.999 and fm == 512
+
+
+def test_two_devices_from_one_thread(gpu_lib, builtin_codes, oracles):
+    """ADVICE (round 1): kernel function attributes (dynamic shared-memory limit) are per DEVICE; the "configured" cache of the
+    launchers is keyed by the device of the code.  One host thread decodes jpl.4096.4.5 (67 KB of dynamic shared memory, above
+    the 48 KB default) on device 0 and then on device 1, batched path, mailbox and simulate.  Needs two visible GPUs."""
+    L = gpu_lib.load()
+    if L.ldpc_b200_device_count() < 2:
+        pytest.skip("one visible GPU")
+    code = builtin_codes["jpl.4096.4.5"]
+    llr = awgn_llrs(code, 3.6, 24, 909, 5120)
+    rb, ri, rc = oracles["jpl.4096.4.5"].decode_batch("min", 20, llr, variant=1)
+    counters = []
+    try:
+        for dev in (0, 1, 0):
+            gpu_lib.init(dev)
+            dc = gpu_lib.DeviceCode(code)
+            for algo in ("min", "spa"):
+                dec = gpu_lib.Decoder(dc, algo, "fp32", max_batch=32)
+                b, it, cv = dec.decode(llr, 20)                               # batched path
+                b1, i1, c1 = dec.decode(llr[:1], 20)                          # mailbox + latency kernel
+                if algo == "min":
+                    assert np.array_equal(b, rb) and np.array_equal(it, ri) and np.array_equal(b1[0], rb[0])
+                    counters.append(dec.simulate(20, 3.4, code.K, 5120, 3, 0, 2000))
+                else:
+                    assert np.array_equal(b1[0], b[0])
+                dec.close()
+            dc.close()
+    finally:
+        gpu_lib.init(0)
+    for c in counters[1:]:
+        assert all(c[k] == counters[0][k] for k in ("frames", "frame_errors", "bit_errors", "sum_iters", "unconverged"))
