@@ -103,9 +103,18 @@ template <typename T, int LO, class Op> struct BoxTree<T, LO, LO + 1, Op> {
 };
 
 #include "spa_fp32.cuh"
-struct OpCompl { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-a, b, a + b); } };
+// 1 - (1 - a)(1 - b) in the form a + b (1 - a): still one FADD + one FFMA and no cancellation, and EXACTLY 1 whenever a or b
+// is exactly 1 (a = 1: b * 0 + 1; b = 1: (1 - a) + a, where 1 - a is exact for a >= 1/2 and otherwise off by at most 2^-25,
+// which the final rounding at 1 absorbs).  That matters: x = 0 (a punctured or erased position, Utils.hs:55) has complement
+// exactly 1, and the reference's product then makes every OTHER message of the check exactly 0 -- so a variable that only
+// hears from such checks keeps lam = 0 and decides 0 (`hard` = (> 0)).  With the symmetric form a + b - a b the "1" came out
+// as 1 - 6e-8, the messages as +-1e-7 with a definite sign, and such variables decided at random: on random codes with
+// erased positions the float32 sum-product agreed with the restatement on only 87-92 % of the frames
+// (tests/test_gpu_parity.py::test_random_user_codes_all_engines; the JPL codes hide it because their punctured columns
+// hear from checks with a single punctured neighbour in the first iteration).
+struct OpCompl { static __device__ __forceinline__ float f(float a, float b) { return fmaf(b, 1.0f - a, a); } };
 // the same on magnitudes (|.| is an operand modifier of FADD / FFMA): leaves may carry a payload in their sign bit
-struct OpComplAbs { static __device__ __forceinline__ float f(float a, float b) { return fmaf(-fabsf(a), fabsf(b), fabsf(a) + fabsf(b)); } };
+struct OpComplAbs { static __device__ __forceinline__ float f(float a, float b) { return fmaf(fabsf(b), 1.0f - fabsf(a), fabsf(a)); } };
 // lg2((2 - c) / c) = 2 atanh(1 - c) / ln 2 (uncapped), and the reference's ceiling 2 * 18.714973875118524 in the same unit
 __device__ __forceinline__ float spa_mag_lg2(float c) { c = fabsf(c); return mufu_lg2(2.0f - c) - mufu_lg2(c); }
 #define SPA_CAP_LG2 54.0f   // 2 * 18.714973875118524 = ln((2 - 2^-53) / 2^-53) = 54 ln 2 to within 1e-16

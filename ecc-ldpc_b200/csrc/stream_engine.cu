@@ -176,17 +176,17 @@ __global__ void k_cn(DeviceGraph g, const T *__restrict__ lam, T *__restrict__ n
             sgn ^= __float_as_uint(x);
             c[k] = spa_compl(x);
             pre[k] = run;
-            run = fmaf(-run, c[k], run + c[k]);
+            run = OpCompl::f(run, c[k]);
             ne[ne_at(b + k, f, g.E)] = (T)x;           // keep x for the sign of the edge
         }
         sgn = ~sgn;
         float suf = 0.0f;
         for (int k = d - 1; k >= 0; k--) {
-            float others = fmaf(-pre[k], suf, pre[k] + suf);
+            float others = OpCompl::f(pre[k], suf);
             float x = (float)ne[ne_at(b + k, f, g.E)];
             float v = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(x)) & 0x80000000u));
             ne[ne_at(b + k, f, g.E)] = (T)v;
-            suf = fmaf(-suf, c[k], suf + c[k]);
+            suf = OpCompl::f(suf, c[k]);
         }
     } else if (ALGO == LDPC_B200_ALGO_SPA_CM) {
         // Fast/CachedMult.hs:248-261: the row's StableDiv product (worst term held out, CachedMult.hs:25-56), folded from
