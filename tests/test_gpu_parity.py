@@ -1114,8 +1114,77 @@ def test_random_user_codes_all_engines(seed, gpu_lib):
         b1, i1, c1 = dec.decode(llr[:3], 15)                                # three frames: mailbox (ONCHIP) / batched (STREAM)
         assert np.array_equal(b1, rb[:3]) and np.array_equal(i1, ri[:3])
         dec.close()
-    sb, si, sc = orc.decode_batch("spa", 15, llr)
-    d32 = gpu_lib.Decoder(dc, "spa", "fp32", max_batch=64)
-    b, it, cv = d32.decode(llr, 15)
-    assert (b == sb).all(axis=1).mean() >= 0.99, (seed, (b == sb).all(axis=1).mean())
-    d32.close(); dc.close()
+    for algo in ("spa", "min"):
+        sb, si, sc = orc.decode_batch(algo, 15, llr, variant=0)
+        d32 = gpu_lib.Decoder(dc, algo, "fp32", max_batch=64)
+        b, it, cv = d32.decode(llr, 15)
+        assert (b == sb).all(axis=1).mean() >= 0.99, (seed, algo, (b == sb).all(axis=1).mean())
+        s32 = gpu_lib.Decoder(dc, algo, "fp32", max_batch=64, engine=gpu_lib.ENGINE_STREAM)
+        b2, it2, cv2 = s32.decode(llr, 15)
+        assert np.array_equal(b, b2) and np.array_equal(it, it2)            # ONCHIP == STREAM in float32 (same arithmetic)
+        d32.close(); s32.close()
+    dc.close()
+
+
+@pytest.mark.parametrize("code_name,n_tx,ebn0", [("jpl.1024.4.5", 1280, 4.6), ("jpl.4096.4.5", 5120, 4.2), ("1920.1280.3.303", None, 3.2)])
+@pytest.mark.parametrize("algo", ["spa", "min"])
+def test_erased_positions_production_engines(code_name, n_tx, ebn0, algo, gpu_lib, dcodes, builtin_codes, oracles):
+    """Erasures: 6 % of the transmitted positions carry LLR exactly 0 (on top of the punctured tail).  An exact zero has
+    tanh = 0 / min' = 0, so every other message of its checks is exactly 0 in the reference, and a variable that hears nothing
+    else keeps lam = 0 and decides 0.  The float32 production kernels (RESIDENT / ONCHIP; complement domain exact at 1, min'
+    exact) reproduce that: decisions on >= 99.9 % of the frames, iteration counts on >= 99 %."""
+    code = builtin_codes[code_name]
+    F = 1024 if algo == "min" else 384
+    llr = awgn_llrs(code, ebn0, F, 60606, n_tx)
+    rng = np.random.default_rng(3)
+    llr[rng.random(llr.shape) < 0.06] = 0.0
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=1024)
+    assert dec.engine() in (gpu_lib.ENGINE_RESIDENT, gpu_lib.ENGINE_ONCHIP)
+    b, it, cv = dec.decode(llr, 30)
+    rb, ri, rc = oracles[code_name].decode_batch(algo, 30, llr, variant=0)
+    assert 0.05 < rc.mean() <= 1.0
+    assert (b == rb).all(axis=1).mean() >= 0.999, (code_name, algo, (b == rb).all(axis=1).mean())
+    assert (it == ri).mean() >= 0.99
+    dec.close()
+
+
+@pytest.mark.parametrize("algo", ["min", "spa"])
+def test_codeword_symmetry_at_config2_batch(algo, gpu_lib, builtin_codes):
+    """Size-independent property at BASELINE config 2's size (jpl.1024.4.5, 16 384 frames in one call): belief propagation on
+    a symmetric channel commutes with adding a codeword -- flipping the LLR signs at the ones of a codeword c flips exactly
+    those decisions and changes nothing else (same iteration count, same convergence flag).  Random messages are encoded on
+    the device (ldpc_b200_ecc_encode_device: Fast/Encoder.hs:41-63 word multiply), the frames of the all-zero codeword come
+    from the device generator, and the float32 production engine decodes both sets."""
+    from ecc_ldpc_b200 import ecc
+    code = builtin_codes["jpl.1024.4.5"]
+    F, K, N, n_tx = 16384, code.K, code.N, 1280
+    name = "ldpc/b200-%s/jpl.1024.4.5/20/4/5" % ("minsum" if algo == "min" else "spa")
+    (e,) = ecc.match(name, max_batch=F)
+    e.run(3.0, 1)                                        # creates the device side of the record
+    rng = np.random.default_rng(77)
+    msgs = rng.integers(0, 2, (F, K)).astype(np.uint8)
+    packed = np.packbits(msgs, axis=1, bitorder="little").view(np.uint32)
+    Wn = (N + 31) // 32
+    d_msg = gpu_lib.DeviceBuffer(packed.nbytes).upload(packed)
+    d_cw = gpu_lib.DeviceBuffer(F * Wn * 4)
+    e.encode_device(d_msg.ptr, d_cw.ptr, F)
+    e.sync()
+    cw = gpu_lib.unpack_bits(d_cw.download(np.uint32, (F, Wn)), N)[:, :n_tx]
+    assert np.array_equal(cw[:, :K], msgs)
+    dc = gpu_lib.DeviceCode(code)
+    dec = gpu_lib.Decoder(dc, algo, "fp32", max_batch=F)
+    assert dec.engine() == gpu_lib.ENGINE_RESIDENT
+    buf = gpu_lib.DeviceBuffer(F * N * 4)
+    dec.generate_llr(buf.ptr, 3.55 if algo == "min" else 3.1, K, n_tx, 5, 0, F)
+    dec.sync()
+    llr0 = buf.download(np.float32, (F, N))
+    llrc = llr0.copy()
+    llrc[:, :n_tx] *= (1.0 - 2.0 * cw).astype(np.float32)
+    p0, i0, c0 = dec.decode_f32(llr0, 20)
+    pc, ic, cc = dec.decode_f32(llrc, 20)
+    b0 = gpu_lib.unpack_bits(p0, N)[:, :n_tx]
+    bc = gpu_lib.unpack_bits(pc, N)[:, :n_tx]
+    assert 0.02 < 1 - c0.mean() < 0.9                    # waterfall: both outcomes present
+    assert np.array_equal(i0, ic) and np.array_equal(c0, cc)
+    assert np.array_equal(bc, b0 ^ cw)
+    dec.close(); dc.close(); e.close()
