@@ -15,6 +15,7 @@
 //     word behind a system-scope fence; every caller spins on ITS slot's word -- no stream synchronisation, no copy engine.
 // Results are those of the batched path bit for bit (same kernels' arithmetic, same float64 -> float32 rounding).
 #include "common.cuh"
+#include <stdio.h>
 #include <string.h>
 #include <atomic>
 #include <chrono>
@@ -56,13 +57,27 @@ struct Mailbox {
     std::string launch_error;
     int refs = 0;
     std::atomic<uint64_t> n_launches{0}, n_frames{0};
+    // LDPC_B200_MB_PROFILE=1: where the time of a call goes (ns, summed over calls; printed when the mailbox is freed)
+    std::atomic<uint64_t> t_copy{0}, t_queue_launch{0}, t_wait{0}, t_unpack{0}, t_calls{0};
 };
+
+static bool mb_profile()
+{
+    static const bool on = [] { const char *e = getenv("LDPC_B200_MB_PROFILE"); return e && e[0] == '1'; }();
+    return on;
+}
 
 static std::mutex g_mb_mu;
 static std::map<std::tuple<const ldpc_b200_code *, int, int, int>, Mailbox *> g_mailboxes;
 
 static void mailbox_free(Mailbox *m)
 {
+    if (mb_profile() && m->t_calls.load()) {
+        const double n = (double)m->t_calls.load();
+        fprintf(stderr, "mailbox profile (N=%d, %llu calls, %llu launches): copy-in %.2f us, queue+launch %.2f us, wait %.2f us, unpack %.2f us per call\n",
+                m->N, (unsigned long long)m->t_calls.load(), (unsigned long long)m->n_launches.load(), m->t_copy.load() / n / 1e3,
+                m->t_queue_launch.load() / n / 1e3, m->t_wait.load() / n / 1e3, m->t_unpack.load() / n / 1e3);
+    }
     cudaSetDevice(m->device);
     for (int i = 0; i < MB_STREAMS; i++) if (m->streams[i]) { cudaStreamSynchronize(m->streams[i]); cudaStreamDestroy(m->streams[i]); }
     if (m->h_llr) cudaFreeHost(m->h_llr);
@@ -205,6 +220,9 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
     if (out_take <= 0 || out_take > N) out_take = N;
     int slots[MB_SLOTS];
     if (n_frames > MB_SLOTS / 4) { set_error("mailbox_decode: batch of %d frames belongs on the batched path", n_frames); return LDPC_B200_EINVAL; }
+    const bool prof = mb_profile();
+    auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const uint64_t p0 = prof ? now_ns() : 0;
     acquire_slots(m, n_frames, slots);
     m->preparing.fetch_add(1, std::memory_order_acq_rel);
     for (int f = 0; f < n_frames; f++) {
@@ -219,6 +237,10 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
         m->n_pending.store((int)m->pending.size(), std::memory_order_release);
     }
     m->preparing.fetch_sub(1, std::memory_order_acq_rel);
+    const uint64_t p1 = prof ? now_ns() : 0;
+    uint64_t p2 = 0, p3 = 0;                              // first launch attempt done / all completion words seen
+    if (prof && m->n_pending.load(std::memory_order_acquire) > 0 && m->launch_mu.try_lock()) { launch_pending(m); m->launch_mu.unlock(); }
+    if (prof) p2 = now_ns();
 
     rc = 0;
     // spin briefly, then yield on every probe: with more callers than cores a spinning waiter would otherwise keep the
@@ -245,6 +267,7 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
         }
         if (rc) break;
         if (v == 0xffffffffu) { set_error("mailbox launch failed: %s", m->launch_error.c_str()); rc = LDPC_B200_ECUDA; break; }
+        if (prof && f == n_frames - 1) p3 = now_ns();
         const uint32_t *pk = m->h_bits + (size_t)s * W;
         if (bits_bytes) {                              // packed word -> one byte per decision, 8 at a time
             uint8_t *o = bits_bytes + (size_t)f * out_take;
@@ -265,6 +288,10 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
     uint64_t give = 0;
     for (int f = 0; f < n_frames; f++) if (rc == 0 || __atomic_load_n(&m->h_done[slots[f]], __ATOMIC_ACQUIRE) != 0) give |= 1ull << slots[f];
     m->free_mask.fetch_or(give, std::memory_order_acq_rel);
+    if (prof && !rc) {
+        const uint64_t p4 = now_ns();
+        m->t_copy += p1 - p0; m->t_queue_launch += p2 - p1; m->t_wait += p3 - p2; m->t_unpack += p4 - p3; m->t_calls += 1;
+    }
     return rc;
 }
 
