@@ -4,8 +4,8 @@
 // Through the batched path such a call costs an H2D copy, a conversion pass, the decode kernel, an unpack pass, a D2H copy
 // and a stream synchronisation: ~80 us, of which the decode itself is less than half, and every thread pays it alone.  Here
 // all decoder handles of one (code, algorithm, precision) share a MAILBOX:
-//   * a small arena of slots in MAPPED pinned host memory: per slot the frame's float64 LLRs (write-combined: the CPU
-//     streams them in, the GPU reads them over PCIe), and its packed decisions / iteration count / flag / completion word;
+//   * a small arena of slots in MAPPED pinned host memory: per slot the frame's float64 LLRs (the CPU copies them in, the
+//     GPU reads them over PCIe), and its packed decisions / iteration count / flag / completion word;
 //   * a caller copies its LLRs into a free slot, queues the slot, and whoever finds the launch lock free becomes the
 //     LEADER: it takes everything queued so far (frames of other threads included -- that is the coalescing), and issues
 //     ONE launch for them on one of a few streams; leadership ends with the launch, not with the completion, so the next
@@ -39,7 +39,7 @@ struct MbPending { int slot, max_iters, take; };
 struct Mailbox {
     const ldpc_b200_code *code = nullptr;
     int device = 0, algo = 0, precision = 0, engine = 0, N = 0, W = 0;
-    double *h_llr = nullptr;               // [MB_SLOTS][N]   write-combined, mapped
+    double *h_llr = nullptr;               // [MB_SLOTS][N]   mapped
     uint32_t *h_bits = nullptr;            // [MB_SLOTS][W]   mapped
     int32_t *h_iters = nullptr;            // [MB_SLOTS]
     uint8_t *h_conv = nullptr;             // [MB_SLOTS]
@@ -97,7 +97,10 @@ static int mailbox_create(ldpc_b200_decoder *d, int engine, Mailbox **out)
     m->ldec.code = d->code; m->ldec.algo = d->algo; m->ldec.precision = d->precision; m->ldec.engine = engine;
     m->ldec.device = d->device; m->ldec.max_batch = MB_SLOTS;
     cudaError_t e = cudaSetDevice(m->device);
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_llr, (size_t)MB_SLOTS * m->N * sizeof(double), cudaHostAllocMapped | cudaHostAllocWriteCombined);
+    // write-combined slots were measured against ordinary (cached) pinned memory: the same for one caller, 3-10 % slower from 16
+    // threads up (16 threads, 2.0 dB: 196-197 k frames/s against 203-218 k) -- the default is cached, LDPC_B200_MB_WC=1 switches
+    static const bool wc = [] { const char *e = getenv("LDPC_B200_MB_WC"); return e && e[0] == '1'; }();
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_llr, (size_t)MB_SLOTS * m->N * sizeof(double), cudaHostAllocMapped | (wc ? cudaHostAllocWriteCombined : 0));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_bits, (size_t)MB_SLOTS * m->W * sizeof(uint32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_iters, MB_SLOTS * sizeof(int32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_conv, MB_SLOTS, cudaHostAllocMapped);
@@ -230,7 +233,7 @@ int mailbox_decode(ldpc_b200_decoder *d, int engine, int max_iters, int n_frames
         memcpy(m->h_llr + (size_t)s * N, llr + (size_t)f * stride, (size_t)take * sizeof(double));
         __atomic_store_n(&m->h_done[s], 0u, __ATOMIC_RELAXED);
     }
-    _mm_sfence();                                       // write-combined stores are globally visible before the slot is queued
+    _mm_sfence();                                       // (write-combined slots: the stores are globally visible before the slot is queued)
     {
         std::lock_guard<std::mutex> lk(m->q_mu);
         for (int f = 0; f < n_frames; f++) m->pending.push_back({slots[f], max_iters, take});
