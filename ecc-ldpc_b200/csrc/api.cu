@@ -313,7 +313,7 @@ void ldpc_b200_shutdown(void)
     }
     for (;;) {
         ldpc_b200_code *c = nullptr;
-        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_codes.empty()) { c = *g_live_codes.begin(); c->refs = 1; } }
+        { std::lock_guard<std::mutex> lk(g_reg_mu); if (!g_live_codes.empty()) { c = *g_live_codes.begin(); c->refs = 1; c->dec_refs = 0; } }
         if (!c) break;
         ldpc_b200_code_destroy(c);
     }
@@ -415,7 +415,8 @@ void ldpc_b200_code_destroy(ldpc_b200_code_t *c)
         std::lock_guard<std::mutex> lk(g_reg_mu);
         auto it = g_live_codes.find(c);
         if (it == g_live_codes.end()) return;              // already released (e.g. by ldpc_b200_shutdown)
-        if (--c->refs > 0) return;                          // other handles still share it
+        if (c->refs > 0) c->refs--;
+        if (c->refs > 0 || c->dec_refs > 0) return;         // other handles share it, or decoders still decode with it
         g_live_codes.erase(it);
     }
     cudaFree(c->g.row_ptr); cudaFree(c->g.col_idx); cudaFree(c->g.col_ptr); cudaFree(c->g.col_edge);
@@ -448,6 +449,7 @@ int ldpc_b200_decoder_create(const ldpc_b200_code_t *code, int algo, int precisi
     if (!d) return LDPC_B200_ENOMEM;
     d->code = code; d->algo = algo; d->precision = precision; d->max_batch = max_batch;
     d->device = code->device;
+    { std::lock_guard<std::mutex> lk(g_reg_mu); const_cast<ldpc_b200_code *>(code)->dec_refs++; }
     reg_add(g_live_decs, d);
     cudaError_t ce = cudaSetDevice(code->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
@@ -508,6 +510,12 @@ void ldpc_b200_decoder_destroy(ldpc_b200_decoder_t *d)
     if (d->ev1) cudaEventDestroy(d->ev1);
     if (d->stream) cudaStreamDestroy(d->stream);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    {   // the code may have lost its last handle while this decoder was alive: then it goes now
+        ldpc_b200_code *c = const_cast<ldpc_b200_code *>(d->code);
+        bool orphan = false;
+        { std::lock_guard<std::mutex> lk(g_reg_mu); if (g_live_codes.count(c)) { c->dec_refs--; orphan = c->refs == 0 && c->dec_refs == 0; } }
+        if (orphan) ldpc_b200_code_destroy(c);
+    }
     delete d;
 }
 

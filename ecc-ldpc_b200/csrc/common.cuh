@@ -53,6 +53,7 @@ struct ldpc_b200_code {
     std::vector<int32_t> shifts;
     int device = -1;
     int refs = 1;                 // handles sharing this object: creating an identical code on the same device returns it again
+    int dec_refs = 0;             // decoders built on it: the object outlives its last handle until they are gone too
     ldpc::DeviceGraph g;          // device copy
     int resident_kind = 0;        // 0 = none, 1 / 2 = compiled RESIDENT specialisation, 3 = run-time table ONCHIP kernel
     // ONCHIP placement, host copy (message tap: slot of reference edge e, position of variable j)

@@ -1188,3 +1188,29 @@ def test_codeword_symmetry_at_config2_batch(algo, gpu_lib, builtin_codes):
     assert np.array_equal(i0, ic) and np.array_equal(c0, cc)
     assert np.array_equal(bc, b0 ^ cw)
     dec.close(); dc.close(); e.close()
+
+
+def test_code_outlives_its_handle_while_decoders_use_it(gpu_lib, builtin_codes, oracles):
+    """Handle lifetimes: identical codes share one device object; destroying a code handle while a decoder still decodes with it
+    leaves the decoder fully usable (the object goes with its last decoder), and destroying handles twice is harmless."""
+    import ctypes as C
+    L = gpu_lib.load()
+    nc, nd = C.c_int(), C.c_int()
+    L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
+    base = (nc.value, nd.value)
+    code = builtin_codes["1920.1280.3.303"]
+    a = gpu_lib.DeviceCode(code)
+    b = gpu_lib.DeviceCode(code)
+    assert a.h == b.h                                                   # one shared object, two handles
+    dec = gpu_lib.Decoder(a, "min", "fp32", max_batch=16)
+    a.close(); b.close()                                                # the decoder keeps the object alive
+    L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
+    assert (nc.value, nd.value) == (base[0], base[1] + 1)
+    llr = awgn_llrs(code, 2.6, 12, 11)
+    rb, ri, rc = oracles["1920.1280.3.303"].decode_batch("min", 20, llr, variant=1)
+    gb, gi, gc = dec.decode(llr, 20)
+    g1, i1, c1 = dec.decode(llr[:1], 20)                                # mailbox path too
+    assert (gb == rb).all(axis=1).mean() >= 0.9 and np.array_equal(g1[0], gb[0])
+    dec.close(); dec.close()
+    L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
+    assert (nc.value, nd.value) == base
