@@ -97,7 +97,11 @@ void ldpc_b200_shutdown(void);
 int ldpc_b200_live_handles(int *codes, int *decoders);
 int ldpc_b200_device_count(void);
 
-/* H as CSR: check m has variables col_idx[row_ptr[m] .. row_ptr[m+1]) in ascending order. Arrays are copied. */
+/* Codes.  Creating a code that is identical (same device, same H) to a live one returns the SAME object with one more handle
+ * reference: mkLDPC builds `maxThreadCount` decoders from the same matrix (Utils.hs:53), which then share one device copy of H
+ * and one mailbox.  ldpc_b200_code_destroy drops one handle reference; the object itself lives until its last handle AND its
+ * last decoder are gone, so the order in which a host destroys codes and decoders does not matter.
+ * H as CSR: check m has variables col_idx[row_ptr[m] .. row_ptr[m+1]) in ascending order. Arrays are copied. */
 int ldpc_b200_code_create_csr(int M, int N, const int32_t *row_ptr, const int32_t *col_idx, ldpc_b200_code_t **out);
 /* H as brows x bcols circulants of size sz: shifts[r*bcols+c] = k means ones at (r*sz+i, c*sz+(i+k)%sz); -1 = zero. */
 int ldpc_b200_code_create_qc(int sz, int brows, int bcols, const int32_t *shifts, ldpc_b200_code_t **out);
