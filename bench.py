@@ -48,10 +48,10 @@ def workload_config(frames_per_step_per_gpu, n_values_per_frame):
             "sharding": "contiguous global frame ranges per rank; one NCCL all-reduce of 5 x u64 error counters per step"}
 
 
-def so_sha256():
-    import hashlib
-    from ecc_ldpc_b200 import lib
-    return hashlib.sha256(open(lib.SO_PATH, "rb").read()).hexdigest()
+def kernel_source_sha256():
+    """Identity of the headline kernel for roofline.traffic (ecc-ldpc_b200/buildinfo.py)."""
+    from ecc_ldpc_b200 import buildinfo
+    return buildinfo.kernel_source_sha256()
 
 
 def alg_bytes_per_frame(code, iters, w=4):
@@ -281,18 +281,18 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = B * b_alg / (k_ms * 1e-3) / 1e9
     # roofline.traffic: dram bytes of ONE launch of the decode kernel from an `ncu --set full` capture, written to
-    # profiles/traffic.json by tools/ncu_traffic.py together with the SHA-256 of the libldpc_b200.so that was profiled.
-    # A capture of another build is NOT reported: traffic = null and the reason is printed.
+    # profiles/traffic.json by tools/ncu_traffic.py together with the SHA-256 of the kernel's sources at capture time.
+    # A capture of other sources is NOT reported: traffic = null and the reason is printed.
     traffic, ncu_static, traffic_note = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("so_sha256") != so_sha256():
-            traffic_note = "profiles/traffic.json was captured from another build of libldpc_b200.so (sha256 %s...); re-run tools/ncu_traffic.py" % str(tj.get("so_sha256"))[:12]
+        if tj.get("kernel_source_sha256") != kernel_source_sha256():
+            traffic_note = "profiles/traffic.json was captured from other kernel sources (sha256 %s...); re-run tools/evidence_r02.sh + tools/publish_evidence_r02.py" % str(tj.get("kernel_source_sha256"))[:12]
             print("bench.py: " + traffic_note, file=sys.stderr)
         else:
             traffic = tj["dram_bytes_per_launch_per_frame"] * B
             ncu_static = tj.get("ncu")
-            traffic_note = "ncu capture %s of kernel %s, same build" % (tj.get("capture"), tj.get("kernel"))
+            traffic_note = "ncu capture %s of kernel %s, same kernel sources (sha256 %s...)" % (tj.get("capture"), tj.get("kernel"), tj["kernel_source_sha256"][:12])
     except Exception as ex:
         traffic_note = "no usable profiles/traffic.json (%r)" % (ex,)
 

@@ -18,5 +18,5 @@ $NCU -k regex:k_vn_tma -s 3 -c 1 -o $O/prof_stream_vn -f python tools/stream_pro
 python tools/stream_probe.py 65536 1920.1280.3.303 min auto > $O/plain_onchip.log 2>&1 && \
 $NCU -k regex:k_onchip -s 1 -c 1 -o $O/prof_onchip -f python tools/stream_probe.py 65536 1920.1280.3.303 min auto > $O/ncu_full_onchip.log 2>&1
 python tools/latency_probe.py 2.0 > $O/latency_probe.log 2>&1
-sha256sum ecc-ldpc_b200/libldpc_b200.so > $O/so.sha256
+python -c "from ecc_ldpc_b200 import buildinfo; print(buildinfo.kernel_source_sha256())" > $O/kernel_sources.sha256
 ls -la $O

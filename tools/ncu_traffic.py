@@ -5,8 +5,9 @@
     ncu -i gpurun_out/r02_resident.ncu-rep --page raw --csv > gpurun_out/r02_resident_raw.csv
     python tools/ncu_traffic.py gpurun_out/r02_resident_raw.csv <frames in the profiled launch> [capture name]
 
-Records the SHA-256 of ecc-ldpc_b200/libldpc_b200.so next to the numbers; bench.py reports roofline.traffic only when that
-hash is the hash of the library it has loaded (a capture of another build is stale by definition)."""
+Records the SHA-256 of the kernel's SOURCES (bench.kernel_source_sha256: the files the RESIDENT kernels are compiled from plus
+the Makefile) next to the numbers; bench.py reports roofline.traffic only when that hash is the hash of the sources in the
+tree (a capture of other sources is stale by definition; the library file's own hash changes with every nvcc run)."""
 import csv, hashlib, json, os, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,7 +36,9 @@ def main():
             i = names.index(k)
             got[short] = float(vals[i].replace(",", "")) * UNIT.get(units[i], 1.0)
     so = os.path.join(ROOT, "ecc-ldpc_b200", "libldpc_b200.so")
-    out = {"so_sha256": hashlib.sha256(open(so, "rb").read()).hexdigest(), "capture": capture, "kernel": kernel, "frames_in_launch": frames,
+    sys.path.insert(0, ROOT)
+    from ecc_ldpc_b200 import buildinfo
+    out = {"kernel_source_sha256": buildinfo.kernel_source_sha256(), "so_sha256_at_capture": hashlib.sha256(open(so, "rb").read()).hexdigest(), "capture": capture, "kernel": kernel, "frames_in_launch": frames,
            "dram_bytes_per_launch": got["dram_read"] + got["dram_write"],
            "dram_bytes_per_launch_per_frame": (got["dram_read"] + got["dram_write"]) / frames,
            "ncu": {k: v for k, v in got.items() if k not in ("dram_read", "dram_write")}}

@@ -52,21 +52,23 @@ def main():
                  ("plain_bench_short.json", "r02_bench_short_for_launch_list.json")):
         shutil.copy(os.path.join(EV, a), os.path.join(PR, b))
     # traffic.json: only if the capture was taken from the library that is in the tree now
-    want = open(os.path.join(EV, "so.sha256")).read().split()[0]
     import hashlib
-    have = hashlib.sha256(open(os.path.join(ROOT, "ecc-ldpc_b200", "libldpc_b200.so"), "rb").read()).hexdigest()
+    sys.path.insert(0, ROOT)
+    from ecc_ldpc_b200 import buildinfo
+    want = open(os.path.join(EV, "kernel_sources.sha256")).read().split()[0]
+    have = buildinfo.kernel_source_sha256()
     raw = subprocess.run(["ncu", "-i", os.path.join(EV, "prof_resident_min.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(EV, "prof_resident_min_raw.csv"), "w").write(raw)
     if want == have:
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), os.path.join(EV, "prof_resident_min_raw.csv"), "32768",
                                "profiles/r02_ncu_resident_minsum.md"])
     else:
-        print("traffic.json NOT written: the capture is of another build (%s... vs %s...)" % (want[:12], have[:12]))
+        print("traffic.json NOT written: the capture is of other kernel sources (%s... vs %s...)" % (want[:12], have[:12]))
     for eng, pats in (("resident", ["k_residentINS_11QcJpl4096P2EfLi1ELi1ELi2ELb0", "k_residentINS_11QcJpl4096P2EfLi1ELi0ELi2ELb0", "k_residentINS_11QcJpl4096P4EfLi1ELi1ELi1ELb0"]),
                       ("stream", ["k_cn_tmaIfLi1ELi18ELi2", "k_vn_tmaIfLi4"]), ("onchip", ["k_onchipIfLi1ELi4ELb1ELi4"])):
         txt = "".join(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_summary.py"), p, "3"], capture_output=True, text=True).stdout for p in pats)
         open(os.path.join(PR, "r02_sass_%s.txt" % eng), "w").write(
-            "# cuobjdump -sass of ecc-ldpc_b200/libldpc_b200.so (sha256 %s), tools/sass_summary.py\n\n%s" % (have, txt))
+            "# cuobjdump -sass of ecc-ldpc_b200/libldpc_b200.so (kernel sources sha256 %s), tools/sass_summary.py\n\n%s" % (have, txt))
 
 
 if __name__ == "__main__":
