@@ -24,7 +24,7 @@ def main():
         ("1920.1280.3.303", "min", 50, None, [(2.0, 2e7), (2.25, 1e8), (2.5, 2e8)]),
         ("1920.1280.3.303", "spa", 50, None, [(1.75, 2e7), (2.0, 5e7)]),
     ]
-    print("# Deep FER / BER points, GPU only (libldpc_b200 float32 production engines), round 1\n")
+    print("# Deep FER / BER points, GPU only (libldpc_b200 float32 production engines), round %s\n" % os.environ.get("LDPC_ROUND", "2"))
     print(__doc__.split("\n\n")[2].strip() + "\n")
     for name, algo, iters, n_tx, pts in configs:
         code = codes.load_builtin(name)
