@@ -46,13 +46,24 @@ template <class C> struct QcMap {
 
 // Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
 // BLK = SZ*sizeof(T) bytes and BLK-aligned, so only the low log2(BLK) bits rotate: one add + one bit-select.
+// RES_ADDR_IMAD: form the add as an integer multiply-add by an opaque 1 (a __constant__ the compiler cannot fold), so that it
+// issues to the FMA pipe (IMAD) instead of the half-rate ALU pipe (VIADD) that the FMNMX trees and the bit-selects live on
+// (46 % of the executed instructions are ALU-pipe instructions; `math_pipe_throttle` is 11 % of the stall samples).
+// Measured (round 2): jpl.1024.4.5 min-sum 21.0 -> 21.7 Gbit/s with all 20 iterations and 40.5 -> 44.6 at 4.0 dB; jpl.4096.4.5
+// min-sum 23.03 -> 23.06 (nothing), sum-product 7.81 -> 7.76.  1: the codes with 32-entry circulants (four frames per CTA), 2: all.
+#ifndef RES_ADDR_IMAD
+#define RES_ADDR_IMAD 1
+#endif
+static __constant__ uint32_t k_opaque_one = 1;
 template <class C, typename T, int S>
 __device__ __forceinline__ uint32_t rot(uint32_t P)
 {
     constexpr uint32_t MASK = C::SZ * sizeof(T) - 1;
     if constexpr (S == 0) return P;
     else {
-        uint32_t y = P + S * (uint32_t)sizeof(T), z;
+        uint32_t y, z;
+        if constexpr (RES_ADDR_IMAD == 2 || (RES_ADDR_IMAD == 1 && C::SZ == 32)) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(y) : "r"(P), "r"(k_opaque_one), "n"(S * (int)sizeof(T)));
+        else y = P + S * (uint32_t)sizeof(T);
         asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(z) : "r"(P), "r"(y), "n"(MASK));   // (P & ~MASK) | (y & MASK)
         return z;
     }
