@@ -9,6 +9,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $NCU -k regex:k_resident -s 2 -c 1 -o $O/prof_resident_min -f python bench.py --steps 2 --warmup 1 --no-extra --no-cpu > $O/ncu_full_min.log 2>&1
 python tools/one_decode.py spa 2.0 16384 1 > $O/plain_spa.log 2>&1 && \
 $NCU -k regex:k_resident -s 1 -c 1 -o $O/prof_resident_spa -f python tools/one_decode.py spa 2.0 16384 1 > $O/ncu_full_spa.log 2>&1
+python tools/quick_bench.py 16384 jpl.1024.4.5 min > $O/plain_min1024.log 2>&1 && \
+$NCU -k regex:k_resident -s 3 -c 1 -o $O/prof_resident_min1024 -f python tools/quick_bench.py 16384 jpl.1024.4.5 min > $O/ncu_full_min1024.log 2>&1
 python tools/one_mailbox.py min 2.0 200 > $O/plain_mailbox.log 2>&1 && \
 $NCU -k regex:k_resident -s 4 -c 1 -o $O/prof_latency_min -f python tools/one_mailbox.py min 2.0 12 > $O/ncu_full_latency.log 2>&1
 python tools/stream_probe.py 8192 > $O/plain_stream.log 2>&1 && \

@@ -18,6 +18,9 @@ REPORTS = [
     ("prof_resident_spa", "r02_ncu_resident_spa.md",
      "ncu --set full: RESIDENT sum-product kernel k_resident<QcJpl4096P2, float, 1, SPA, 2, false> (round 2; 16384 frames, 20 iterations, Eb/N0 2.0 dB)",
      NCU + " -k regex:k_resident -s 1 -c 1 python tools/one_decode.py spa 2.0 16384 1"),
+    ("prof_resident_min1024", "r02_ncu_resident_minsum_jpl1024.md",
+     "ncu --set full: RESIDENT min-sum kernel k_resident<QcJpl1024P2, float, 4, MINSUM, 2, false> (BASELINE config 2: jpl.1024.4.5, 16384 frames, four frames per CTA, all 20 iterations, Eb/N0 2.0 dB)",
+     NCU + " -k regex:k_resident -s 3 -c 1 python tools/quick_bench.py 16384 jpl.1024.4.5 min"),
     ("prof_latency_min", "r02_ncu_latency_minsum.md",
      "ncu --set full: latency instance k_resident<QcJpl4096P4, float, 1, MINSUM, 1, false> behind the mailbox (ONE frame = one CTA of 512 threads, 20 iterations, LLRs read from mapped host memory)",
      NCU + " -k regex:k_resident -s 4 -c 1 python tools/one_mailbox.py min 2.0 12"),
