@@ -110,6 +110,24 @@ template <class C, typename T> struct Lay {
 #ifndef RES_FUSE_SCALE
 #define RES_FUSE_SCALE 1
 #endif
+// Base-2 units (float32 sum-product): the whole frame state -- channel LLRs, posteriors, messages -- is kept in units of ln 2
+// (x2 = x * log2 e, scaled once when the frame comes in).  The check update then needs no scaling on either side: the input
+// complement is 1 / (1/2 + 2^|x2| / 2) (EX2, FFMA, RCP; before: FFMA, EX2, FADD, RCP), the output magnitude
+// lg2((2 - c) / c) is already in the stored unit (before: times ln 2), and the reference's clamp is exactly 54.  Two
+// FMA-pipe instructions fewer per edge and iteration; decisions depend on signs only; the message tap scales back.
+#ifndef RES_SPA_LOG2
+#define RES_SPA_LOG2 1
+#endif
+__device__ __forceinline__ float spa_compl2(float x2) { return mufu_rcp(fmaf(mufu_ex2(fabsf(x2)), 0.5f, 0.5f)); }
+__device__ __forceinline__ float spa_mag2(float c) { return fminf(mufu_lg2(2.0f - c) - mufu_lg2(c), SPA_CAP_LG2); }
+template <typename T, int ALGO> struct Units {
+    static constexpr bool LOG2 = RES_SPA_LOG2 && sizeof(T) == 4 && ALGO == LDPC_B200_ALGO_SPA;
+    static __device__ __forceinline__ T in(T llr) { if constexpr (LOG2) return __fmul_rn(llr, 1.4426950408889634f); else return llr; }
+    static __device__ __forceinline__ T out(T v) { if constexpr (LOG2) return __fmul_rn(v, 0.69314718055994531f); else return v; }
+    static __device__ __forceinline__ float compl_of(float x) { if constexpr (LOG2) return spa_compl2(x); else return spa_compl(x); }
+    static __device__ __forceinline__ float mag_of(float c) { if constexpr (LOG2) return spa_mag2(c); else return spa_mag(c); }
+};
+
 template <typename T, int ALGO> struct MsgForm {
     static constexpr bool FUSED = RES_FUSE_SCALE && sizeof(T) == 4 && ALGO == LDPC_B200_ALGO_MINSUM;
     // x of the next check phase from the stored message s and the (negated) posterior
@@ -128,7 +146,7 @@ template <typename T, int ALGO> struct MsgForm {
     }
     static __device__ __forceinline__ T value(T s)                 // the reference's ne' (message tap)
     {
-        if constexpr (FUSED) return __fmul_rn(-0.75f, s); else return s;
+        if constexpr (FUSED) return __fmul_rn(-0.75f, s); else return Units<T, ALGO>::out(s);
     }
 };
 
@@ -177,11 +195,11 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
             static_for<d>([&](auto ki) { sgn ^= __float_as_uint(ne[base + decltype(ki)::value]); });
             sgn = ~sgn;                                                // leading minus times the product of ALL signs
             BoxTree<float, 0, d, OpCompl> tree;
-            tree.build([&](auto ki) { return spa_compl(ne[base + decltype(ki)::value]); });
+            tree.build([&](auto ki) { return Units<T, ALGO>::compl_of(ne[base + decltype(ki)::value]); });
             tree.down_root([&](auto ki, float others) {
                 constexpr int k = decltype(ki)::value;
                 // own sign removed from the product: sgn ^ sign(x_k); magnitude >= 0 so its sign bit is free
-                ne[base + k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                ne[base + k] = __uint_as_float(__float_as_uint(Units<T, ALGO>::mag_of(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
             });
         }
     });
@@ -299,10 +317,10 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
                 unsat |= par;
                 sgn = ~sgn;
                 BoxTree<float, 0, d, OpCompl> tree;
-                tree.build([&](auto ki) { return spa_compl(ne[base + decltype(ki)::value]); });
+                tree.build([&](auto ki) { return Units<float, LDPC_B200_ALGO_SPA>::compl_of(ne[base + decltype(ki)::value]); });
                 tree.down_root([&](auto ki, float others) {
                     constexpr int k = decltype(ki)::value;
-                    ne[base + k] = __uint_as_float(__float_as_uint(spa_mag(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                    ne[base + k] = __uint_as_float(__float_as_uint(Units<float, LDPC_B200_ALGO_SPA>::mag_of(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
                 });
             }
         });
@@ -333,7 +351,7 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
         const uint32_t cap_s = (~sgn & 0x80000000u) | __float_as_uint(SPA_CAP_LG2);
         static_for<D>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
-            xs[k] = __uint_as_float(__float_as_uint(spa_compl(xs[k])) | (__float_as_uint(xs[k]) & 0x80000000u));
+            xs[k] = __uint_as_float(__float_as_uint(Units<float, LDPC_B200_ALGO_SPA>::compl_of(xs[k])) | (__float_as_uint(xs[k]) & 0x80000000u));
         });
         BoxTree<float, 0, D, OpComplAbs> tree;
         tree.build([&](auto ki) { return xs[decltype(ki)::value]; });
@@ -345,7 +363,10 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
         dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
             constexpr int idx = decltype(ci)::value;
             constexpr int base = QcMap<C>::reg_base(BigRows<C>::row(idx / NB, idx % NB));
-            static_for<D>([&](auto ki) { ne[base + decltype(ki)::value] = xs[decltype(ki)::value] * 0.69314718055994531f; });
+            static_for<D>([&](auto ki) {
+                if constexpr (RES_SPA_LOG2) ne[base + decltype(ki)::value] = xs[decltype(ki)::value];            // already in the stored unit
+                else ne[base + decltype(ki)::value] = xs[decltype(ki)::value] * 0.69314718055994531f;
+            });
         });
     }
     return unsat & F::SIGN;
@@ -550,7 +571,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
         if constexpr (TRACE) {
             if (f == 0 && p.trace_lam) {        // lam' = -mu (Orig.hs:95-98); every stage ended behind a barrier
                 T *out = reinterpret_cast<T *>(p.trace_lam) + (size_t)n * N;
-                for (int j = tf; j < N; j += TPF) out[j] = -mu[Lay<C, T>::mu_index(j)];
+                for (int j = tf; j < N; j += TPF) out[j] = Units<T, ALGO>::out(-mu[Lay<C, T>::mu_index(j)]);
             }
         }
     }
@@ -615,7 +636,7 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
         if (prefetch) {
             mbar_wait(mbar, phase);
             phase ^= 1u;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, stage[j]); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(stage[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
             bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
             if (tf == 0) {
                 const unsigned int nxt = atomicAdd(p.work, 1u);
@@ -624,12 +645,12 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
             }
         } else if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)fi * N;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, src[j]); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(src[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
             bar_sync(bar, TPF);
         } else if (p.llr64) {
             // the reference's float64 vector, rounded to T exactly as the host-side conversion would; unpuncture (Utils.hs:55)
             const double *src = p.llr64 + (size_t)fi * p.llr64_stride;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, j < p.llr64_take ? (T)src[j] : (T)0); negL[j] = v; put_mu(j, v); }
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, j < p.llr64_take ? Units<T, ALGO>::in((T)src[j]) : (T)0); negL[j] = v; put_mu(j, v); }
             bar_sync(bar, TPF);
         } else {
             for (int g = tf; g < N / 4; g += TPF) {
@@ -638,7 +659,7 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     int j = 4 * g + q;
-                    T v = F::sub((T)0, (j < p.n_tx) ? (T)awgn_llr(nz[q], 0, p.sigma, p.scale) : (T)0);
+                    T v = F::sub((T)0, (j < p.n_tx) ? Units<T, ALGO>::in((T)awgn_llr(nz[q], 0, p.sigma, p.scale)) : (T)0);
                     negL[j] = v; put_mu(j, v);
                 }
             }
