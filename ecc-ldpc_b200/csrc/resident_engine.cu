@@ -37,6 +37,7 @@
 #include "philox.cuh"
 #include <atomic>
 #include <utility>
+#include <type_traits>
 
 // RES_PARTS: threads per check position (2 or 4). More parts = fewer message registers per thread = more resident
 // warps to hide shared-memory latency, at the price of more barrier participants.
@@ -129,7 +130,7 @@ __global__ void k_convert_f64(const double *__restrict__ in, T *__restrict__ out
 template <class C, typename T, int FPC, int ALGO>
 static int launch(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream, bool static_grid)
 {
-    return launch_instance<C, T, FPC, ALGO, sizeof(T) == 4 ? 2 : 1, false>(d, p, stream, static_grid);
+    return launch_instance<typename PlanFor<C, T, ALGO>::type, T, FPC, ALGO, sizeof(T) == 4 ? 2 : 1, false>(d, p, stream, static_grid);
 }
 
 template <typename T, int ALGO>

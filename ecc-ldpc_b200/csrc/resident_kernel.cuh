@@ -29,19 +29,106 @@ template <class C> struct QcMap {
     }
     static constexpr int NEH = max_part_edges();
     static constexpr int N = C::BC * C::SZ;
-    // edge (r, k) is the LAST link of its column's chain (the first block row of the column): the thread that finishes
-    // the new posterior of that variable is also the one that reads it for edge (r, k) in the next check phase
-    static __host__ __device__ constexpr bool is_final_edge(int r, int k)
-    {
-        int c = C::row_col[r][k];
-        return C::col_row_desc[c][C::col_deg[c] - 1] == r;
-    }
     static __host__ __device__ constexpr int local_row(int r)       // index of row r inside its part
     {
         int h = C::half_of_row[r];
         for (int q = 0; q < C::HR; q++) if (C::half_rows[h][q] == r) return q;
         return -1;
     }
+};
+
+// Variable-phase plan.  RES_VN_PLAN names one of the short-chain plans of qc_tables.inc (VN2, VN3, VN4: S stages;
+// VNC1, VNC2, VNC3: singletons stored in the check phase); undefined: the original schedule, one link per stage
+// (col_stage, S = maximum column degree).  A plan says for every step q of column c's chain (col_row_desc order:
+// innermost link first) in which stage it runs and what it is:
+//   chain (0)     load the running value (negL for q = 0), apply the own message, store it back -- as always;
+//   singleton (1) store the own message as it is into a slot of its own behind negL (no load);
+//   final (2)     load the running value (or negL) AND the column's singleton slots, apply them in chain order, then the
+//                 own message: the finished posterior.
+// The operands, their order and every rounding are those of the reference's right fold (Orig.hs:95-98) under every plan --
+// only who executes a link changes -- so all plans produce the same bits (float64: the reference restatement's); shared-memory operations
+// are d loads + d stores per column under every plan; what changes is the number of barriers per iteration, 1 + S.
+template <class C> struct VnLegacy {
+    static constexpr int S = C::MAXCD, NSLOT = 0;
+    static __host__ __device__ constexpr int stage_of(int c, int q)
+    {
+        for (int t = 0; t < C::MAXCD; t++) if (C::col_stage[c][t] == q) return t;
+        return -9;
+    }
+    static __host__ __device__ constexpr int kind_of(int c, int q) { return q < C::col_deg[c] - 1 ? 0 : 2; }
+    static __host__ __device__ constexpr int slot_of(int, int) { return -1; }
+};
+template <class C, class V> struct VnTable {
+    static constexpr int S = V::S, NSLOT = V::NSLOT;
+    static __host__ __device__ constexpr int stage_of(int c, int q) { return V::stage[c][q]; }
+    static __host__ __device__ constexpr int kind_of(int c, int q) { return V::kind[c][q]; }
+    static __host__ __device__ constexpr int slot_of(int c, int q) { return V::slot[c][q]; }
+};
+// A code struct with a plan attached: the kernels are instantiated on WithPlan<code tables, plan tables> (or on the bare
+// code struct: original schedule).
+struct VnNone {};
+template <class C0, class V> struct WithPlan : C0 { typedef V VN; typedef C0 Base; };
+template <class C, class = void> struct VnPlanSel { typedef VnLegacy<C> type; };
+template <class C> struct VnPlanSel<C, std::void_t<typename C::VN>> { typedef VnTable<C, typename C::VN> type; };
+template <class C0> struct VnPlanSel<WithPlan<C0, VnNone>, void> { typedef VnLegacy<C0> type; };
+template <class C> using VnPlan = typename VnPlanSel<C>::type;
+// Which plan serves which instance.  RES_VN_PLAN (default VNC2, the measured best: profiles/r02_vn_plans.md) for the
+// throughput and message-tap instances -- float32 min-sum, float32 sum-product, float64 --, each overridable
+// (RES_VN_PLAN_MIN / _SPA / _F64); the four-part latency instances keep the original schedule unless RES_VN_PLAN_LAT names
+// a plan (measured: no difference, 43 us per 20-iteration frame either way).  RES_VN_LEGACY: original schedule everywhere.
+#ifndef RES_VN_PLAN
+#define RES_VN_PLAN VNC2
+#endif
+#ifndef RES_VN_LEGACY
+#ifndef RES_VN_PLAN_MIN
+#define RES_VN_PLAN_MIN RES_VN_PLAN
+#endif
+#ifndef RES_VN_PLAN_SPA
+#define RES_VN_PLAN_SPA RES_VN_PLAN
+#endif
+#ifndef RES_VN_PLAN_F64
+#define RES_VN_PLAN_F64 RES_VN_PLAN
+#endif
+#endif
+// LAT: instance of resident_latency.cu
+template <class C0, typename T, int ALGO, bool LAT = false> struct PlanFor { typedef WithPlan<C0, VnNone> type; };
+#ifdef RES_VN_PLAN_MIN
+template <class C0> struct PlanFor<C0, float, LDPC_B200_ALGO_MINSUM, false> { typedef WithPlan<C0, typename C0::RES_VN_PLAN_MIN> type; };
+#endif
+#ifdef RES_VN_PLAN_SPA
+template <class C0> struct PlanFor<C0, float, LDPC_B200_ALGO_SPA, false> { typedef WithPlan<C0, typename C0::RES_VN_PLAN_SPA> type; };
+#endif
+#ifdef RES_VN_PLAN_F64
+template <class C0, int ALGO> struct PlanFor<C0, double, ALGO, false> { typedef WithPlan<C0, typename C0::RES_VN_PLAN_F64> type; };
+#endif
+#ifdef RES_VN_PLAN_LAT
+template <class C0, int ALGO> struct PlanFor<C0, float, ALGO, true> { typedef WithPlan<C0, typename C0::RES_VN_PLAN_LAT> type; };
+#endif
+template <class C> struct VnEdge {
+    // step of edge (r, k) in its column's chain
+    static __host__ __device__ constexpr int step(int r, int k)
+    {
+        int c = C::row_col[r][k];
+        for (int q = 0; q < C::col_deg[c]; q++) if (C::col_row_desc[c][q] == r) return q;
+        return -1;
+    }
+    static __host__ __device__ constexpr int nchain(int c)
+    {
+        int n = 0;
+        for (int q = 0; q < C::col_deg[c]; q++) n += VnPlan<C>::kind_of(c, q) == 0;
+        return n;
+    }
+    // edge (r, k) belongs to the thread that FINISHES the new posterior of its variable (the executor of the column's plan;
+    // originally the last link = the first block row of the column): the same thread reads it for edge (r, k) in the next
+    // check phase, which is what the last-link fold uses
+    static __host__ __device__ constexpr bool is_final_edge(int r, int k) { return VnPlan<C>::kind_of(C::row_col[r][k], step(r, k)) == 2; }
+    // singleton stored in the check phase?
+    static __host__ __device__ constexpr bool cn_single(int r, int k)
+    {
+        int c = C::row_col[r][k], q = step(r, k);
+        return VnPlan<C>::kind_of(c, q) == 1 && VnPlan<C>::stage_of(c, q) < 0;
+    }
+    static __host__ __device__ constexpr int slot(int r, int k) { return VnPlan<C>::slot_of(C::row_col[r][k], step(r, k)); }
 };
 
 // Shared address of variable (c = 0, (i+s) mod SZ) given P = address of variable (0, i): the block column is
@@ -90,7 +177,15 @@ template <class C, typename T> struct Lay {
     static constexpr int N = C::BC * C::SZ;
     static constexpr int MUE = RES_DUP ? 2 * N : N;               // elements of mu per frame
     static constexpr int NEGL = MUE * (int)sizeof(T);             // byte offset of negL behind mu (block columns of BLK bytes)
-    static constexpr int FS = MUE + N;                            // elements of mu + negL per frame
+    static constexpr int SLOT0 = NEGL + N * (int)sizeof(T);       // byte offset of the singleton slots behind negL (BLK bytes each)
+    static constexpr int FS = MUE + N + VnPlan<C>::NSLOT * C::SZ; // elements of mu + negL + singleton slots per frame
+    // Does the frame state PLUS a staging row for the next frame's LLRs fit MINB CTAs of FPC frames per SM (227 KB, 1 KB
+    // reserved per CTA, 128 bytes of bookkeeping)?  If not -- plans with many singleton slots -- the CTA has no staging row:
+    // the next frame's row is only warmed in L2 (cp.async.bulk.prefetch.L2) and read with plain loads when its turn comes.
+    static __host__ __device__ constexpr bool staged(int FPC, int MINB)
+    {
+        return (long long)MINB * ((long long)FPC * (FS + N) * (long long)sizeof(T) + 1024 + 128) <= 227 * 1024;
+    }
     static __host__ __device__ constexpr int mu_index(int j) { return RES_DUP ? j + (j & ~(C::SZ - 1)) : j; }   // variable j in mu
     // mu of variable (c, (i + S) mod SZ) for the thread whose P = address of mu entry (0, i)
     template <int c, int S> static __device__ __forceinline__ T lds_mu(uint32_t P)
@@ -150,6 +245,14 @@ template <typename T, int ALGO> struct MsgForm {
     }
 };
 
+// A singleton whose plan puts its store into the check phase: right after the row's new messages exist.
+template <class C, typename T, int r, int k>
+__device__ __forceinline__ void cn_store_single(T v, uint32_t P)
+{
+    if constexpr (VnEdge<C>::cn_single(r, k))
+        FB<T>::template sts<Lay<C, T>::SLOT0 + VnEdge<C>::slot(r, k) * Lay<C, T>::BLK>(rot<C, T, C::row_shift[r][k]>(P), v);
+}
+
 // Shared memory holds mu = -lam (the NEGATED posterior) and negL = 0 - L.  Negation is exact and symmetric under
 // round-to-nearest, so mu is bit for bit the negation of the reference's lam, with one useful difference: an exact
 // zero (punctured LLR, or a sum that cancels) is +0.0 in mu, and mu is never -0.0 (x + y = -0 needs both operands
@@ -177,7 +280,7 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
             constexpr int k = decltype(ki)::value;
             constexpr int c = C::row_col[r][k];
             constexpr int s = C::row_shift[r][k];
-            if constexpr (!(FOLD && QcMap<C>::is_final_edge(r, k))) {
+            if constexpr (!(FOLD && VnEdge<C>::is_final_edge(r, k))) {
                 T m = Lay<C, T>::template lds_mu<c, s>(P);
                 par ^= F::bits(m);
                 ne[base + k] = MsgForm<T, ALGO>::x_of(ne[base + k], m);     // x = -(lam_j - ne[m,j]) = ne + mu   (Min.hs:80)
@@ -188,7 +291,11 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
             // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
             BoxTree<T, 0, d> tree;
             tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
-            tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = MsgForm<T, ALGO>::store(others); });
+            tree.down_root([&](auto ki, T others) {
+                constexpr int k = decltype(ki)::value;
+                ne[base + k] = MsgForm<T, ALGO>::store(others);
+                cn_store_single<C, T, r, k>(ne[base + k], P);
+            });
         } else if constexpr (sizeof(T) == 4) {
             // ne'[m,n] = -2 atanh'(product [ tanh(x_j / 2) | j /= n ])   (Orig.hs:86-91), complement-domain form
             uint32_t sgn = 0;
@@ -200,6 +307,7 @@ __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], ty
                 constexpr int k = decltype(ki)::value;
                 // own sign removed from the product: sgn ^ sign(x_k); magnitude >= 0 so its sign bit is free
                 ne[base + k] = __uint_as_float(__float_as_uint(Units<T, ALGO>::mag_of(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                cn_store_single<C, T, r, k>(ne[base + k], P);
             });
         }
     });
@@ -228,7 +336,7 @@ __device__ __forceinline__ typename FB<T>::B cn_gather(T (&ne)[QcMap<C>::NEH], t
         if constexpr (FOLD) { par = fpar[decltype(qi)::value]; fpar[decltype(qi)::value] = 0; }
         static_for<C::row_deg[r]>([&](auto ki) {
             constexpr int k = decltype(ki)::value;
-            if constexpr (!(FOLD && QcMap<C>::is_final_edge(r, k))) {
+            if constexpr (!(FOLD && VnEdge<C>::is_final_edge(r, k))) {
                 T m = Lay<C, T>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P);
                 par ^= F::bits(m);
                 ne[base + k] = MsgForm<T, ALGO>::x_of(ne[base + k], m);
@@ -239,7 +347,7 @@ __device__ __forceinline__ typename FB<T>::B cn_gather(T (&ne)[QcMap<C>::NEH], t
     return unsat & F::SIGN;
 }
 template <class C, typename T, int H, int ALGO>
-__device__ __forceinline__ void cn_trees(T (&ne)[QcMap<C>::NEH])
+__device__ __forceinline__ void cn_trees(T (&ne)[QcMap<C>::NEH], uint32_t P)
 {
     static_for<C::HR>([&](auto qi) {
         constexpr int r = C::half_rows[H][decltype(qi)::value];
@@ -247,7 +355,11 @@ __device__ __forceinline__ void cn_trees(T (&ne)[QcMap<C>::NEH])
         constexpr int base = QcMap<C>::reg_base(r);
         BoxTree<T, 0, d> tree;                                      // ne'[m,n] = (-3/4) * foldr1 min' [ x_j | j /= n ]   (Min.hs:79-87)
         tree.build([&](auto ki) { return ne[base + decltype(ki)::value]; });
-        tree.down_root([&](auto ki, T others) { ne[base + decltype(ki)::value] = MsgForm<T, ALGO>::store(others); });
+        tree.down_root([&](auto ki, T others) {
+            constexpr int k = decltype(ki)::value;
+            ne[base + k] = MsgForm<T, ALGO>::store(others);
+            cn_store_single<C, T, r, k>(ne[base + k], P);
+        });
     });
 }
 
@@ -321,6 +433,7 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
                 tree.down_root([&](auto ki, float others) {
                     constexpr int k = decltype(ki)::value;
                     ne[base + k] = __uint_as_float(__float_as_uint(Units<float, LDPC_B200_ALGO_SPA>::mag_of(others)) | ((sgn ^ __float_as_uint(ne[base + k])) & 0x80000000u));
+                    cn_store_single<C, float, r, k>(ne[base + k], P);
                 });
             }
         });
@@ -362,10 +475,13 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
         });
         dispatch_index<0, C::NP * NB>(sel, [&](auto ci) {
             constexpr int idx = decltype(ci)::value;
-            constexpr int base = QcMap<C>::reg_base(BigRows<C>::row(idx / NB, idx % NB));
+            constexpr int rb = BigRows<C>::row(idx / NB, idx % NB);
+            constexpr int base = QcMap<C>::reg_base(rb);
             static_for<D>([&](auto ki) {
-                if constexpr (RES_SPA_LOG2) ne[base + decltype(ki)::value] = xs[decltype(ki)::value];            // already in the stored unit
-                else ne[base + decltype(ki)::value] = xs[decltype(ki)::value] * 0.69314718055994531f;
+                constexpr int k = decltype(ki)::value;
+                if constexpr (RES_SPA_LOG2) ne[base + k] = xs[k];            // already in the stored unit
+                else ne[base + k] = xs[k] * 0.69314718055994531f;
+                cn_store_single<C, float, rb, k>(ne[base + k], P);
             });
         });
     }
@@ -393,47 +509,79 @@ __device__ __forceinline__ typename FB<T>::B synd_phase(uint32_t P)
 }
 
 // Variable-node stage Q for part H.  Column c builds mu' = (-ne'[m1]) + ((-ne'[m2]) + ... ((-ne'[mk]) + negL)), the
-// exact negation of Orig.hs:95-98, one link per stage from the innermost (last block row) outwards; col_stage
-// says which link runs in which stage.  negL sits Lay::NEGL bytes after mu.
+// exact negation of Orig.hs:95-98, from the innermost link (last block row) outwards; VnPlan says which step of which
+// column runs in which stage and how (chain link / singleton store / final fold, see VnPlan).  negL sits Lay::NEGL bytes
+// after mu, the singleton slots Lay::SLOT0 bytes after it.
+// RES_VN_CHUNKS: the columns of a stage are processed in this many groups, each "all loads, then all stores" (inside a
+// stage no address is touched by two threads, so the groups need no barrier); bounds the live temporaries of a long stage.
+#ifndef RES_VN_CHUNKS
+#define RES_VN_CHUNKS 2
+#endif
 template <class C, typename T, int H, int Q, bool FOLD, int ALGO>
 __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
 {
     typedef FB<T> F;
-    constexpr int BLK = Lay<C, T>::BLK, CB = Lay<C, T>::CB, NEGL = Lay<C, T>::NEGL;
-    // Two passes: every load of the stage is issued before the first store.  The accesses are volatile asm and keep
-    // their program order, so a fused load-subtract-store per link would serialise the stage on shared-memory latency.
-    T acc[C::BC];
-    static_for<C::BC>([&](auto ci) {
-        constexpr int c = decltype(ci)::value;
-        constexpr int step = C::col_stage[c][Q];          // which link of column c's chain runs in this stage
-        if constexpr (step >= 0) {
-            constexpr int r = C::col_row_desc[c][step];
-            if constexpr (C::half_of_row[r] == H) {
-                constexpr int k = C::col_k_desc[c][step];
-                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                acc[c] = (step == 0) ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * CB>(a);
-            }
-        }
-    });
-    static_for<C::BC>([&](auto ci) {
-        constexpr int c = decltype(ci)::value;
-        constexpr int step = C::col_stage[c][Q];
-        if constexpr (step >= 0) {
-            constexpr int r = C::col_row_desc[c][step];
-            if constexpr (C::half_of_row[r] == H) {
-                constexpr int k = C::col_k_desc[c][step];
-                constexpr int e = QcMap<C>::reg_base(r) + k;
-                uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
-                const T val = MsgForm<T, ALGO>::link(acc[c], ne[e]);
-                F::template sts<c * CB>(a, val);
-                if constexpr (RES_DUP && step == C::col_deg[c] - 1) F::template sts<c * CB + BLK>(a, val);      // the finished posterior: both halves
-                if constexpr (FOLD && step == C::col_deg[c] - 1) {
-                    // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
-                    ne[e] = MsgForm<T, ALGO>::x_of(ne[e], val);                  // x of the next check phase
-                    fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
+    typedef VnPlan<C> V;
+    constexpr int BLK = Lay<C, T>::BLK, CB = Lay<C, T>::CB, NEGL = Lay<C, T>::NEGL, SLOT0 = Lay<C, T>::SLOT0;
+    constexpr int MAXS = C::MAXCD;                               // indexed by chain step
+    constexpr int PER = (C::BC + RES_VN_CHUNKS - 1) / RES_VN_CHUNKS;
+    static_for<RES_VN_CHUNKS>([&](auto gi) {
+        constexpr int C0 = decltype(gi)::value * PER, C1 = (C0 + PER < C::BC) ? C0 + PER : C::BC;
+        // Two passes: every load of the group is issued before the first store.  The accesses are volatile asm and keep
+        // their program order, so a fused load-subtract-store per link would serialise the stage on shared-memory latency.
+        T acc[PER];
+        T sg[PER][MAXS];
+        static_for<C1 - C0>([&](auto ci) {
+            constexpr int c = C0 + decltype(ci)::value;
+            static_for<C::col_deg[c]>([&](auto qi) {
+                constexpr int q = decltype(qi)::value;
+                constexpr int r = C::col_row_desc[c][q];
+                constexpr int kind = V::kind_of(c, q);
+                if constexpr (V::stage_of(c, q) == Q && C::half_of_row[r] == H && kind != 1) {
+                    const uint32_t a = rot<C, T, C::row_shift[r][C::col_k_desc[c][q]]>(P);
+                    constexpr bool from_negL = (kind == 0) ? (q == 0) : (VnEdge<C>::nchain(c) == 0);
+                    acc[c - C0] = from_negL ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * CB>(a);
+                    if constexpr (kind == 2) {
+                        static_for<C::col_deg[c]>([&](auto q2i) {
+                            constexpr int q2 = decltype(q2i)::value;
+                            if constexpr (V::kind_of(c, q2) == 1) sg[c - C0][q2] = F::template lds<SLOT0 + V::slot_of(c, q2) * BLK>(a);
+                        });
+                    }
                 }
-            }
-        }
+            });
+        });
+        static_for<C1 - C0>([&](auto ci) {
+            constexpr int c = C0 + decltype(ci)::value;
+            static_for<C::col_deg[c]>([&](auto qi) {
+                constexpr int q = decltype(qi)::value;
+                constexpr int r = C::col_row_desc[c][q];
+                constexpr int kind = V::kind_of(c, q);
+                if constexpr (V::stage_of(c, q) == Q && C::half_of_row[r] == H) {
+                    constexpr int k = C::col_k_desc[c][q];
+                    constexpr int e = QcMap<C>::reg_base(r) + k;
+                    const uint32_t a = rot<C, T, C::row_shift[r][k]>(P);
+                    if constexpr (kind == 0) {
+                        F::template sts<c * CB>(a, MsgForm<T, ALGO>::link(acc[c - C0], ne[e]));
+                    } else if constexpr (kind == 1) {
+                        F::template sts<SLOT0 + V::slot_of(c, q) * BLK>(a, ne[e]);           // the message as it is; the final link applies it
+                    } else {
+                        T val = acc[c - C0];
+                        static_for<C::col_deg[c]>([&](auto q2i) {                         // the rest of the chain, in chain order
+                            constexpr int q2 = decltype(q2i)::value;
+                            if constexpr (V::kind_of(c, q2) == 1) val = MsgForm<T, ALGO>::link(val, sg[c - C0][q2]);
+                            else if constexpr (q2 == q) val = MsgForm<T, ALGO>::link(val, ne[e]);
+                        });
+                        F::template sts<c * CB>(a, val);
+                        if constexpr (RES_DUP) F::template sts<c * CB + BLK>(a, val);      // the finished posterior: both halves
+                        if constexpr (FOLD) {
+                            // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
+                            ne[e] = MsgForm<T, ALGO>::x_of(ne[e], val);                  // x of the next check phase
+                            fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
+                        }
+                    }
+                }
+            });
+        });
     });
 }
 
@@ -454,7 +602,7 @@ template <class C> struct RefEdge {
 // form, whose big-row arithmetic is shared: cn_phase_spa_looped); table-dependent phases branch on h (warp-uniform).
 // TRACE: message tap of launch frame 0 (ldpc_b200_decode_trace).  (The output index of the frame -- f or its mailbox slot --
 // and the staging row of the packed decisions are recomputed where the frame finishes: nothing extra stays live in the loop.)
-template <class C, typename T, int H, int ALGO, bool TRACE, int FPC>
+template <class C, typename T, int H, int ALGO, bool TRACE, int FPC, bool STAGED>
 __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned int f, const T *mu, const T *negL, uint32_t P,
                                              int bar, int tf, int lane, FrameCounters &cnt, int h = H)
 {
@@ -475,7 +623,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             constexpr int r = C::half_rows[H][decltype(qi)::value];
             static_for<C::row_deg[r]>([&](auto ki) {
                 constexpr int k = decltype(ki)::value;
-                if constexpr (Mp::is_final_edge(r, k)) {
+                if constexpr (VnEdge<C>::is_final_edge(r, k)) {
                     T m = Lay<C, T>::template lds_mu<C::row_col[r][k], C::row_shift[r][k]>(P);
                     ne[Mp::reg_base(r) + k] = m;
                     fpar[decltype(qi)::value] ^= FB<T>::bits(m);
@@ -506,8 +654,11 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             // syndrome ok -> hard(lam); iterations exhausted -> hard(orig_lam)   (Orig.hs:68-71)
             done = true;
             const unsigned int fi = p.use_map ? p.slot_map[f] : f;
-            // the staging row of this slot (see k_resident): stage - negL = (FPC - slot) * FS - MUE + slot * N
-            uint32_t *obuf = reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC - (bar - 1)) * Lay<C, T>::FS - Lay<C, T>::MUE + (size_t)(bar - 1) * N);
+            // the staging row of this slot (see k_resident): stage - negL = (FPC - slot) * FS - MUE + slot * N; without a staging
+            // row: the frame's singleton slots, which are dead once the frame has finished
+            static_assert(STAGED || VnPlan<C>::NSLOT * C::SZ * sizeof(T) >= (N / 32) * sizeof(uint32_t), "no room to stage the packed decisions");
+            uint32_t *obuf = STAGED ? reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC - (bar - 1)) * Lay<C, T>::FS - Lay<C, T>::MUE + (size_t)(bar - 1) * N)
+                                    : reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + N);
             unsigned int errs = 0;
             for (int w = wif; w < W; w += WPF) {
                 const int j = 32 * w + lane;
@@ -542,7 +693,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             }
         }
         if (n == p.max_iters || (done && p.early_exit)) break;
-        if constexpr (H >= 0 && RES_VOTE_FIRST && ALGO == LDPC_B200_ALGO_MINSUM) cn_trees<C, T, H, ALGO>(ne);
+        if constexpr (H >= 0 && RES_VOTE_FIRST && ALGO == LDPC_B200_ALGO_MINSUM) cn_trees<C, T, H, ALGO>(ne, P);
 
         if constexpr (TRACE) {
             // message tap: ne' of this iteration in reference edge order (Orig.hs:81-92 / Min.hs:75-87), before the last-link
@@ -562,7 +713,7 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
         }
 
         // ---- variable phase ----
-        static_for<C::MAXCD>([&](auto qi) {
+        static_for<VnPlan<C>::S>([&](auto qi) {
             if constexpr (H >= 0) vn_stage<C, T, H, decltype(qi)::value, FOLD, ALGO>(ne, fpar, P);
             else dispatch_index<0, C::NP>(h, [&](auto hi) { vn_stage<C, T, decltype(hi)::value, decltype(qi)::value, false, ALGO>(ne, fpar, P); });
             bar_sync(bar, TPF);
@@ -594,8 +745,9 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
     T *negL = mu + MUE;                                                  // negated channel LLRs
     // staging row of the NEXT frame's LLRs (host-supplied frames only): fetched by one bulk copy while this frame decodes;
     // in mailbox mode (no prefetch) the same row stages the packed decisions
+    constexpr bool STAGED = Lay<C, T>::staged(FPC, MINB);               // see Lay::staged
     T *stage = reinterpret_cast<T *>(smem_raw) + (size_t)FPC * FS + (size_t)slot * N;
-    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * (FS + N));
+    unsigned int *s_next = reinterpret_cast<unsigned int *>(reinterpret_cast<T *>(smem_raw) + (size_t)FPC * (FS + (STAGED ? N : 0)));
     uint64_t *mbar = reinterpret_cast<uint64_t *>(s_next + ((FPC + 1) & ~1)) + slot;
     const uint32_t P = (uint32_t)__cvta_generic_to_shared(mu + i);
     auto put_mu = [&](int j, T v) {                       // initial posterior of variable j (both halves of a duplicated column)
@@ -607,12 +759,17 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
 
     FrameCounters cnt;
     uint32_t phase = 0;
+    // fetch of the row of frame nxt: into the staging row (completes on mbar), or -- no staging row -- into L2 only
+    auto fetch_row = [&](unsigned int nxt) {
+        if constexpr (STAGED) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+        else bulk_prefetch_l2(reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB);
+    };
     if (prefetch) {
         if (tf == 0) {
-            mbar_init(mbar, 1);
+            if constexpr (STAGED) mbar_init(mbar, 1);
             const unsigned int nxt = atomicAdd(p.work, 1u);
             s_next[slot] = nxt;
-            if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+            if (nxt < p.n_frames) fetch_row(nxt);
         }
         bar_sync(bar, TPF);
     }
@@ -634,14 +791,15 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
 
         // ---- frame in: negL = 0 - L, mu = negL ----
         if (prefetch) {
-            mbar_wait(mbar, phase);
-            phase ^= 1u;
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(stage[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
+            const T *row = stage;
+            if constexpr (STAGED) { mbar_wait(mbar, phase); phase ^= 1u; }
+            else row = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;     // warmed in L2 while the previous frame decoded
+            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(row[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
             bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
             if (tf == 0) {
                 const unsigned int nxt = atomicAdd(p.work, 1u);
                 s_next[slot] = nxt;             // read at the top of the next round, many barriers from here
-                if (nxt < p.n_frames) { mbar_expect_tx(mbar, ROWB); bulk_g2s(stage, reinterpret_cast<const T *>(p.llr) + (size_t)nxt * N, ROWB, mbar); }
+                if (nxt < p.n_frames) fetch_row(nxt);
             }
         } else if (p.llr) {
             const T *src = reinterpret_cast<const T *>(p.llr) + (size_t)fi * N;
@@ -667,15 +825,15 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
         }
 
         if constexpr (ALGO == LDPC_B200_ALGO_SPA && sizeof(T) == 4 && RES_SPA_LOOPED) {
-            decode_frame<C, T, -1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt, h);
+            decode_frame<C, T, -1, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt, h);
         } else if constexpr (C::NP == 2) {
-            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else decode_frame<C, T, 1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 1, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
         } else {
-            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else if (h == 1) decode_frame<C, T, 1, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else if (h == 2) decode_frame<C, T, 2, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
-            else decode_frame<C, T, 3, ALGO, TRACE, FPC>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            if (h == 0) decode_frame<C, T, 0, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 1) decode_frame<C, T, 1, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else if (h == 2) decode_frame<C, T, 2, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
+            else decode_frame<C, T, 3, ALGO, TRACE, FPC, STAGED>(p, f, mu, negL, P, bar, tf, lane, cnt);
         }
         // all smem reads of this frame are done before the next frame's values arrive: decode_frame ends behind a barrier
     }
@@ -699,7 +857,7 @@ static int launch_instance(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t
 {
     typedef QcMap<C> Mp;
     auto kern = k_resident<C, T, FPC, ALGO, MINB, TRACE>;
-    size_t smem = (size_t)FPC * (Lay<C, T>::FS + Mp::N) * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
+    size_t smem = (size_t)FPC * (Lay<C, T>::FS + (Lay<C, T>::staged(FPC, MINB) ? Mp::N : 0)) * sizeof(T) + ((FPC + 1) & ~1) * sizeof(unsigned int) + FPC * sizeof(uint64_t);
     static_assert((C::SZ * sizeof(T)) <= 1024, "block columns must fit the 1024-byte alignment of the smem base");
     static std::atomic<int> cfg_bps[MAX_DEVICES], cfg_sm[MAX_DEVICES];
     const int dev = d->code->device;

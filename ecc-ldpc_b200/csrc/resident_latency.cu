@@ -8,6 +8,7 @@
 #include "philox.cuh"
 #include <atomic>
 #include <utility>
+#include <type_traits>
 
 #ifndef RES_SPA_LOOPED
 #define RES_SPA_LOOPED 1
@@ -28,8 +29,8 @@ template <int ALGO>
 static int latency_kind(ldpc_b200_decoder *d, ResidentParams &p, cudaStream_t stream)
 {
     switch (d->code->resident_kind) {
-    case 1: return launch_instance<QcJpl1024P4, float, 1, ALGO, 1, false>(d, p, stream, true);
-    case 2: return launch_instance<QcJpl4096P4, float, 1, ALGO, 1, false>(d, p, stream, true);
+    case 1: return launch_instance<typename PlanFor<QcJpl1024P4, float, ALGO, true>::type, float, 1, ALGO, 1, false>(d, p, stream, true);
+    case 2: return launch_instance<typename PlanFor<QcJpl4096P4, float, ALGO, true>::type, float, 1, ALGO, 1, false>(d, p, stream, true);
     default: set_error("no RESIDENT specialisation for this code"); return LDPC_B200_EUNSUPPORTED;
     }
 }

@@ -8,6 +8,7 @@
 #include "philox.cuh"
 #include <atomic>
 #include <utility>
+#include <type_traits>
 
 #ifndef RES_SPA_LOOPED
 #define RES_SPA_LOOPED 1
@@ -28,8 +29,8 @@ template <typename T, int ALGO>
 static int trace_kind(ldpc_b200_decoder *d, ResidentParams &p)
 {
     switch (d->code->resident_kind) {
-    case 1: return launch_instance<QcJpl1024P2, T, 4, ALGO, sizeof(T) == 4 ? 2 : 1, true>(d, p, d->stream, true);
-    case 2: return launch_instance<QcJpl4096P2, T, 1, ALGO, sizeof(T) == 4 ? 2 : 1, true>(d, p, d->stream, true);
+    case 1: return launch_instance<typename PlanFor<QcJpl1024P2, T, ALGO>::type, T, 4, ALGO, sizeof(T) == 4 ? 2 : 1, true>(d, p, d->stream, true);
+    case 2: return launch_instance<typename PlanFor<QcJpl4096P2, T, ALGO>::type, T, 1, ALGO, sizeof(T) == 4 ? 2 : 1, true>(d, p, d->stream, true);
     default: set_error("no RESIDENT specialisation for this code"); return LDPC_B200_EUNSUPPORTED;
     }
 }

@@ -110,6 +110,146 @@ def schedule_stages(cols_desc, owner, NP, T, seed=1):
     return table, best // 1000
 
 
+def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exec_rule="any", shifts=None, long_chain=False):
+    """Variable-node plan with S stages (S < the maximum column degree).  Column c of degree d applies the FIRST
+    l <= min(d-1, S-1) links of its chain (innermost first) one per stage as before; of the remaining steps one is the
+    column's EXECUTOR and the others are SINGLETONS: a singleton's thread only stores its raw message into a slot of its
+    own (no load), in a stage before the executor's -- or, with cn_single, already in the check phase (stage -1); the
+    executor loads the chain value (or negL) and the singleton slots and folds them together with its own message IN CHAIN
+    ORDER, so the arithmetic -- operands, order, roundings -- is exactly that of the one-link-per-stage schedule
+    (Orig.hs:95-98); only who performs it changes.  Shared-memory operations are the same under every plan (d loads + d
+    stores per column); barriers per iteration drop from 1 + max degree to 1 + S.  Local search over (l, executor,
+    stages) per column, minimising the sum over stages of the busiest part, with at most max_slots singleton slots.
+    Returns per-step tables stage / kind (0 chain, 1 singleton, 2 executor) / slot, the number of slots and the loads."""
+    import random
+    rng = random.Random(seed)
+    BC = len(cols_desc)
+    degs = [len(c) for c in cols_desc]
+    lo_single = -1 if cn_single else 0
+
+    def random_assign(d, c):
+        l = min(d - 1, S - 1) if long_chain else rng.randint(0, min(d - 1, S - 1))
+        st = sorted(rng.sample(range(S), l + 1))               # chain stages..., executor stage
+        tf = st[-1]
+        ns = d - 1 - l
+        if ns > 0 and tf - 1 < lo_single:
+            return None
+        if exec_rule == "top":                                 # the column's first block row, as in the original schedule
+            qf = d - 1
+        elif exec_rule == "zero":                              # an identity circulant if there is one behind the chain (its thread
+            z = [q for q in range(l, d) if shifts[cols_desc[c][q]][c] == 0]        # needs no address arithmetic)
+            qf = rng.choice(z) if z else rng.randint(l, d - 1)
+        elif exec_rule == "nonzero":
+            z = [q for q in range(l, d) if shifts[cols_desc[c][q]][c] != 0]
+            qf = rng.choice(z) if z else rng.randint(l, d - 1)
+        else:
+            qf = rng.randint(l, d - 1)
+        stage = []
+        for q in range(d):
+            if q < l:
+                stage.append(st[q])
+            elif q == qf:
+                stage.append(tf)
+            else:
+                stage.append(-1 if cn_single else rng.randint(lo_single, tf - 1))
+        return (l, qf, stage)
+
+    def initial(d, c):
+        # the plan with the fewest slots: longest chain
+        for _ in range(100000):
+            a = random_assign(d, c)
+            if a is not None and a[0] == min(d - 1, S - 1):
+                return a
+        raise SystemExit("no feasible plan: S=%d cn_single=%s degree %d" % (S, cn_single, d))
+
+    choice = [initial(d, c) for c, d in enumerate(degs)]
+
+    def slots(ch):
+        return sum(degs[c] - 1 - a[0] for c, a in enumerate(ch))
+
+    def contrib(c, a, L, sign):
+        l, qf, st = a
+        d = degs[c]
+        for q, t in enumerate(st):
+            w = 2 if q < l else (2 + (d - 1 - l) if q == qf else 1)
+            L[t if t >= 0 else S][owner[cols_desc[c][q]]] += sign * w
+
+    def loads(ch):
+        L = [[0] * NP for _ in range(S + 1)]                   # index S: the check phase (stage -1)
+        for c, a in enumerate(ch):
+            contrib(c, a, L, +1)
+        return L
+
+    def cost_of(L, nslots):
+        over = max(0, nslots - max_slots)
+        return (over * 100000 + sum(max(row) for row in L[:S]) * 1000 + sum(max(row) - min(row) for row in L[:S]) * 10 +
+                (max(L[S]) - min(L[S])) * 10 + (max(max(row) for row in L[:S]) - min(max(row) for row in L[:S])))
+
+    L = loads(choice)
+    ns = slots(choice)
+    best = cost_of(L, ns)
+    for it in range(200000):
+        c = rng.randrange(BC)
+        new = random_assign(degs[c], c)
+        if new is None:
+            continue
+        old = choice[c]
+        contrib(c, old, L, -1)
+        contrib(c, new, L, +1)
+        ns2 = ns - (degs[c] - 1 - old[0]) + (degs[c] - 1 - new[0])
+        v = cost_of(L, ns2)
+        if v <= best:
+            best = v
+            ns = ns2
+            choice[c] = new
+        else:
+            contrib(c, new, L, -1)
+            contrib(c, old, L, +1)
+    assert slots(choice) <= max_slots, "slot budget not met"
+    maxcd = max(degs)
+    stage = [[-9] * maxcd for _ in range(BC)]
+    kind = [[-1] * maxcd for _ in range(BC)]
+    slot = [[-1] * maxcd for _ in range(BC)]
+    nslot = 0
+    for c, (l, qf, st) in enumerate(choice):
+        for q, t in enumerate(st):
+            stage[c][q] = t
+            kind[c][q] = 0 if q < l else (2 if q == qf else 1)
+            if kind[c][q] == 1:
+                slot[c][q] = nslot
+                nslot += 1
+    validate_plan(cols_desc, S, cn_single, stage, kind, slot, nslot)
+    return stage, kind, slot, nslot, loads(choice)
+
+
+def validate_plan(cols_desc, S, cn_single, stage, kind, slot, nslot):
+    """Structural proof obligations of a plan (what makes it equal to the one-link-per-stage schedule bit for bit):
+    chain links are a prefix of the chain in strictly increasing stages; exactly one executor per column, behind the
+    chain and in a later stage than every chain link; every other step is a singleton with a slot of its own, stored
+    before the executor's stage (in the check phase, stage -1, only if the plan allows it)."""
+    seen = set()
+    for c, rows in enumerate(cols_desc):
+        d = len(rows)
+        ks = [kind[c][q] for q in range(d)]
+        l = 0
+        while l < d and ks[l] == 0:
+            l += 1
+        assert all(k in (1, 2) for k in ks[l:]) and ks.count(2) == 1, (c, ks)
+        chain_st = [stage[c][q] for q in range(l)]
+        assert all(0 <= t < S for t in chain_st) and chain_st == sorted(set(chain_st)), (c, chain_st)
+        tf = stage[c][ks.index(2)]
+        assert 0 <= tf < S and all(t < tf for t in chain_st), (c, tf, chain_st)
+        for q in range(d):
+            if ks[q] == 1:
+                assert (-1 if cn_single else 0) <= stage[c][q] < tf, (c, q, stage[c][q], tf)
+                assert 0 <= slot[c][q] < nslot and slot[c][q] not in seen
+                seen.add(slot[c][q])
+            else:
+                assert slot[c][q] == -1
+        assert all(kind[c][q] == -1 for q in range(d, len(kind[c])))
+    assert len(seen) == nslot
+
+
 def emit(name, ident, out, NP=2):
     d = json.load(open(os.path.join(CODES, name + ".json")))
     sh = d["h_shifts"]
@@ -141,8 +281,28 @@ def emit(name, ident, out, NP=2):
     out.append("    static constexpr int col_k_desc[BC][MAXCD] = %s;" % arr2([pad(c, maxcd) for c in col_k]))
     out.append("    // col_stage[c][t] = chain step (index into col_row_desc[c]) that column c applies in VN stage t, -1 = idle")
     out.append("    static constexpr int col_stage[BC][MAXCD] = %s;" % arr2(col_stage))
+    # short-chain plans (see plan_short_chains): VN<S> with singleton stores in the variable stages, VNC<S> with the
+    # singleton stores in the check phase
+    for S, cn_single, max_slots, rule, long_chain, seed, tag in PLANS:
+        stage, kind, slot, nslot, L = plan_short_chains(cols_desc, half_of_row, NP, S, cn_single, max_slots, seed=seed, exec_rule=rule, shifts=sh, long_chain=long_chain)
+        out.append("    // %s: %d stages%s, %d singleton slots; shared-memory operations per stage and part %s%s" %
+                   (tag, S, ", singletons stored in the check phase" if cn_single else "", nslot, L[:S],
+                    ", check phase %s" % L[S] if cn_single else ""))
+        out.append("    struct %s {" % tag)
+        out.append("        static constexpr int S = %d, NSLOT = %d;" % (S, nslot))
+        out.append("        static constexpr int stage[BC][MAXCD] = %s;" % arr2(stage).replace("\n        ", "\n            "))
+        out.append("        static constexpr int kind[BC][MAXCD] = %s;" % arr2(kind).replace("\n        ", "\n            "))
+        out.append("        static constexpr int slot[BC][MAXCD] = %s;" % arr2(slot).replace("\n        ", "\n            "))
+        out.append("    };")
     out.append("};")
     out.append("")
+
+
+# (stages, singleton stores in the check phase, slot budget, executor rule, longest chains only, seed, name)
+# VNC2 is the production plan (measured best of the family on B200, profiles/r02_vn_plans.md): two stages, 92 slots -- what
+# fits two CTAs per SM next to the staging row --, executor = the column's first block row (mostly identity circulants);
+# VNC2T: longest chains (72 slots); VNC1: no chains at all, one stage, 112 slots (no room for a staging row).
+PLANS = [(2, True, 92, "top", False, 3, "VNC2"), (2, True, 72, "top", True, 1, "VNC2T"), (1, True, 112, "zero", True, 1, "VNC1")]
 
 
 def main():

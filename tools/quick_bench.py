@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Kernel-only timing of the RESIDENT decode for tuning: python tools/quick_bench.py [frames] [code]
 (LDPC_B200_SO selects a library variant)."""
-import os, sys
+import os, sys, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from ecc_ldpc_b200 import codes, lib
@@ -28,6 +28,8 @@ for ebn0, ee in ((2.0, True), (4.0, True)):
         dec.sync()
         ms.append(dec.last_timing()[0])
     m = float(np.median(ms[3:]))
-    avg_it = it.download(np.int32, (F,)).mean()
-    out.append("ebn0 %.1f: %.3f ms  %.3f Mframes/s  %.2f Gbit/s  avg_it %.2f" % (ebn0, m, F / m / 1e3, F / m / 1e3 * code.K / 1e3, avg_it))
+    its = it.download(np.int32, (F,))
+    avg_it = its.mean()
+    crc = zlib.crc32(its.tobytes(), zlib.crc32(bits.download(np.uint32, (F, code.N // 32)).tobytes()))   # same decisions <=> same crc (variants)
+    out.append("ebn0 %.1f: %.3f ms  %.3f Mframes/s  %.2f Gbit/s  avg_it %.2f crc %08x" % (ebn0, m, F / m / 1e3, F / m / 1e3 * code.K / 1e3, avg_it, crc))
 print(os.environ.get("LDPC_B200_SO", "default"), name, algo, "engine", dec.engine(), "|", " | ".join(out))
