@@ -112,6 +112,13 @@ template <class C> struct VnEdge {
         for (int q = 0; q < C::col_deg[c]; q++) if (C::col_row_desc[c][q] == r) return q;
         return -1;
     }
+    // the executor's steps of column c (kind 2) all belong to one thread; the LAST of them carries the executor's code
+    static __host__ __device__ constexpr int exec_primary(int c)
+    {
+        int p = -1;
+        for (int q = 0; q < C::col_deg[c]; q++) if (VnPlan<C>::kind_of(c, q) == 2) p = q;
+        return p;
+    }
     static __host__ __device__ constexpr int nchain(int c)
     {
         int n = 0;
@@ -537,7 +544,7 @@ __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>:
                 constexpr int q = decltype(qi)::value;
                 constexpr int r = C::col_row_desc[c][q];
                 constexpr int kind = V::kind_of(c, q);
-                if constexpr (V::stage_of(c, q) == Q && C::half_of_row[r] == H && kind != 1) {
+                if constexpr (V::stage_of(c, q) == Q && C::half_of_row[r] == H && (kind == 0 || (kind == 2 && q == VnEdge<C>::exec_primary(c)))) {
                     const uint32_t a = rot<C, T, C::row_shift[r][C::col_k_desc[c][q]]>(P);
                     constexpr bool from_negL = (kind == 0) ? (q == 0) : (VnEdge<C>::nchain(c) == 0);
                     acc[c - C0] = from_negL ? F::template lds<NEGL + c * BLK>(a) : F::template lds<c * CB>(a);
@@ -564,19 +571,31 @@ __device__ __forceinline__ void vn_stage(T (&ne)[QcMap<C>::NEH], typename FB<T>:
                         F::template sts<c * CB>(a, MsgForm<T, ALGO>::link(acc[c - C0], ne[e]));
                     } else if constexpr (kind == 1) {
                         F::template sts<SLOT0 + V::slot_of(c, q) * BLK>(a, ne[e]);           // the message as it is; the final link applies it
-                    } else {
+                    } else if constexpr (q == VnEdge<C>::exec_primary(c)) {
+                        // the executor: the rest of the chain in chain order -- slots of the other threads' edges, registers
+                        // for its own (edges of this variable in other block rows of this part with the same shift)
                         T val = acc[c - C0];
-                        static_for<C::col_deg[c]>([&](auto q2i) {                         // the rest of the chain, in chain order
+                        static_for<C::col_deg[c]>([&](auto q2i) {
                             constexpr int q2 = decltype(q2i)::value;
                             if constexpr (V::kind_of(c, q2) == 1) val = MsgForm<T, ALGO>::link(val, sg[c - C0][q2]);
-                            else if constexpr (q2 == q) val = MsgForm<T, ALGO>::link(val, ne[e]);
+                            else if constexpr (V::kind_of(c, q2) == 2) {
+                                constexpr int e2 = QcMap<C>::reg_base(C::col_row_desc[c][q2]) + C::col_k_desc[c][q2];
+                                val = MsgForm<T, ALGO>::link(val, ne[e2]);
+                            }
                         });
                         F::template sts<c * CB>(a, val);
                         if constexpr (RES_DUP) F::template sts<c * CB + BLK>(a, val);      // the finished posterior: both halves
                         if constexpr (FOLD) {
-                            // last link: val is the new mu of this variable, and edge e is this thread's own edge into it
-                            ne[e] = MsgForm<T, ALGO>::x_of(ne[e], val);                  // x of the next check phase
-                            fpar[QcMap<C>::local_row(r)] ^= F::bits(val);                // its hard decision, for the next syndrome
+                            // val is the new mu of this variable, and the executor's edges are this thread's own edges into it
+                            static_for<C::col_deg[c]>([&](auto q2i) {
+                                constexpr int q2 = decltype(q2i)::value;
+                                if constexpr (V::kind_of(c, q2) == 2) {
+                                    constexpr int r2 = C::col_row_desc[c][q2];
+                                    constexpr int e2 = QcMap<C>::reg_base(r2) + C::col_k_desc[c][q2];
+                                    ne[e2] = MsgForm<T, ALGO>::x_of(ne[e2], val);            // x of the next check phase
+                                    fpar[QcMap<C>::local_row(r2)] ^= F::bits(val);           // its hard decision, for the next syndrome
+                                }
+                            });
                         }
                     }
                 }

@@ -24,8 +24,9 @@ def arr2(rows):
 
 
 def split_rows(shifts, NP):
-    """Partition the block rows into NP parts with equal edge counts, minimising sum over VN stages of the
-    largest per-part stage work (every stage ends in a barrier, so the slowest part sets its length)."""
+    """Partition the block rows into NP parts with equal edge counts: first maximise the number of edges the column
+    executors can fold in registers (see cost), then minimise the sum over the original VN stages of the largest per-part
+    stage work (every stage ends in a barrier, so the slowest part sets its length)."""
     BR, BC = len(shifts), len(shifts[0])
     deg = [sum(1 for v in row if v >= 0) for row in shifts]
     cols = [sorted((r for r in range(BR) if shifts[r][c] >= 0), reverse=True) for c in range(BC)]
@@ -47,7 +48,17 @@ def split_rows(shifts, NP):
                 if len(c) > q:
                     cnt[owner[c[q]]] += 1
             tot += max(cnt)
-        return tot
+        # edges of one variable that fall to the SAME thread (same part, same shift) are folded in registers by the column's
+        # executor: each saves a slot store, a slot load and a posterior load per iteration (plan_short_chains) -- worth far
+        # more than stage balance, so it leads the objective
+        merged = 0
+        for c in range(BC):
+            groups = {}
+            for r in cols[c]:
+                key = (owner[r], shifts[r][c])
+                groups[key] = groups.get(key, 0) + 1
+            merged += max(groups.values()) - 1
+        return tot - 1000 * merged
 
     def rec(remaining, parts):
         if not remaining:
@@ -126,52 +137,71 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
     BC = len(cols_desc)
     degs = [len(c) for c in cols_desc]
     lo_single = -1 if cn_single else 0
+    # Same-thread groups: steps of a column whose edges belong to one thread (same part, same shift).  If a column has
+    # such a group of two or more, that thread is the executor and ALL the group's messages are its own registers.
+    exec_group = []
+    for c, rows in enumerate(cols_desc):
+        groups = {}
+        for q, r in enumerate(rows):
+            groups.setdefault((owner[r], shifts[r][c]), []).append(q)
+        best_g = max(groups.values(), key=lambda g: (len(g), shifts[rows[g[0]]][c] == 0, max(g)))
+        exec_group.append(best_g if len(best_g) > 1 else None)
 
     def random_assign(d, c):
-        l = min(d - 1, S - 1) if long_chain else rng.randint(0, min(d - 1, S - 1))
+        G = exec_group[c]
+        first = min(G) if G else d - 1                         # chain links come before the executor's first own step
+        lmax = min(first, S - 1)
+        l = lmax if long_chain else rng.randint(0, lmax)
         st = sorted(rng.sample(range(S), l + 1))               # chain stages..., executor stage
         tf = st[-1]
-        ns = d - 1 - l
-        if ns > 0 and tf - 1 < lo_single:
-            return None
-        if exec_rule == "top":                                 # the column's first block row, as in the original schedule
-            qf = d - 1
+        if G:
+            ex = list(G)
+        elif exec_rule == "top":                               # the column's first block row, as in the original schedule
+            ex = [d - 1]
         elif exec_rule == "zero":                              # an identity circulant if there is one behind the chain (its thread
             z = [q for q in range(l, d) if shifts[cols_desc[c][q]][c] == 0]        # needs no address arithmetic)
-            qf = rng.choice(z) if z else rng.randint(l, d - 1)
+            ex = [rng.choice(z) if z else rng.randint(l, d - 1)]
         elif exec_rule == "nonzero":
             z = [q for q in range(l, d) if shifts[cols_desc[c][q]][c] != 0]
-            qf = rng.choice(z) if z else rng.randint(l, d - 1)
+            ex = [rng.choice(z) if z else rng.randint(l, d - 1)]
         else:
-            qf = rng.randint(l, d - 1)
+            ex = [rng.randint(l, d - 1)]
+        ns = d - l - len(ex)
+        if ns > 0 and tf - 1 < lo_single:
+            return None
         stage = []
         for q in range(d):
             if q < l:
                 stage.append(st[q])
-            elif q == qf:
+            elif q in ex:
                 stage.append(tf)
             else:
                 stage.append(-1 if cn_single else rng.randint(lo_single, tf - 1))
-        return (l, qf, stage)
+        return (l, tuple(ex), stage)
 
     def initial(d, c):
         # the plan with the fewest slots: longest chain
         for _ in range(100000):
             a = random_assign(d, c)
-            if a is not None and a[0] == min(d - 1, S - 1):
+            if a is not None and a[0] == min(min(exec_group[c]) if exec_group[c] else d - 1, S - 1):
                 return a
         raise SystemExit("no feasible plan: S=%d cn_single=%s degree %d" % (S, cn_single, d))
 
     choice = [initial(d, c) for c, d in enumerate(degs)]
 
     def slots(ch):
-        return sum(degs[c] - 1 - a[0] for c, a in enumerate(ch))
+        return sum(degs[c] - a[0] - len(a[1]) for c, a in enumerate(ch))
 
     def contrib(c, a, L, sign):
-        l, qf, st = a
+        l, ex, st = a
         d = degs[c]
         for q, t in enumerate(st):
-            w = 2 if q < l else (2 + (d - 1 - l) if q == qf else 1)
+            if q < l:
+                w = 2
+            elif q in ex:
+                w = 2 + (d - l - len(ex)) if q == ex[-1] else 0    # the executor: chain value + slots in, posterior out
+            else:
+                w = 1
             L[t if t >= 0 else S][owner[cols_desc[c][q]]] += sign * w
 
     def loads(ch):
@@ -182,7 +212,9 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
 
     def cost_of(L, nslots):
         over = max(0, nslots - max_slots)
-        return (over * 100000 + sum(max(row) for row in L[:S]) * 1000 + sum(max(row) - min(row) for row in L[:S]) * 10 +
+        # (a singleton's store overlaps the trees of the check phase, a chain link is two operations in a stage: at equal
+        # stage cost prefer the plan with more singletons)
+        return (over * 100000 - nslots * 400 + sum(max(row) for row in L[:S]) * 1000 + sum(max(row) - min(row) for row in L[:S]) * 10 +
                 (max(L[S]) - min(L[S])) * 10 + (max(max(row) for row in L[:S]) - min(max(row) for row in L[:S])))
 
     L = loads(choice)
@@ -196,7 +228,7 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
         old = choice[c]
         contrib(c, old, L, -1)
         contrib(c, new, L, +1)
-        ns2 = ns - (degs[c] - 1 - old[0]) + (degs[c] - 1 - new[0])
+        ns2 = ns - (degs[c] - old[0] - len(old[1])) + (degs[c] - new[0] - len(new[1]))
         v = cost_of(L, ns2)
         if v <= best:
             best = v
@@ -211,22 +243,23 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
     kind = [[-1] * maxcd for _ in range(BC)]
     slot = [[-1] * maxcd for _ in range(BC)]
     nslot = 0
-    for c, (l, qf, st) in enumerate(choice):
+    for c, (l, ex, st) in enumerate(choice):
         for q, t in enumerate(st):
             stage[c][q] = t
-            kind[c][q] = 0 if q < l else (2 if q == qf else 1)
+            kind[c][q] = 0 if q < l else (2 if q in ex else 1)
             if kind[c][q] == 1:
                 slot[c][q] = nslot
                 nslot += 1
-    validate_plan(cols_desc, S, cn_single, stage, kind, slot, nslot)
+    validate_plan(cols_desc, owner, shifts, S, cn_single, stage, kind, slot, nslot)
     return stage, kind, slot, nslot, loads(choice)
 
 
-def validate_plan(cols_desc, S, cn_single, stage, kind, slot, nslot):
+def validate_plan(cols_desc, owner, shifts, S, cn_single, stage, kind, slot, nslot):
     """Structural proof obligations of a plan (what makes it equal to the one-link-per-stage schedule bit for bit):
-    chain links are a prefix of the chain in strictly increasing stages; exactly one executor per column, behind the
-    chain and in a later stage than every chain link; every other step is a singleton with a slot of its own, stored
-    before the executor's stage (in the check phase, stage -1, only if the plan allows it)."""
+    chain links are a prefix of the chain in strictly increasing stages; the executor steps of a column all belong to ONE
+    thread (same part, same shift), lie behind the chain and run in a later stage than every chain link; every other step
+    is a singleton with a slot of its own, stored before the executor's stage (in the check phase, stage -1, only if the
+    plan allows it)."""
     seen = set()
     for c, rows in enumerate(cols_desc):
         d = len(rows)
@@ -234,10 +267,13 @@ def validate_plan(cols_desc, S, cn_single, stage, kind, slot, nslot):
         l = 0
         while l < d and ks[l] == 0:
             l += 1
-        assert all(k in (1, 2) for k in ks[l:]) and ks.count(2) == 1, (c, ks)
+        assert all(k in (1, 2) for k in ks[l:]) and ks.count(2) >= 1, (c, ks)
+        ex = [q for q in range(d) if ks[q] == 2]
+        assert len({(owner[rows[q]], shifts[rows[q]][c]) for q in ex}) == 1, (c, ex)
+        assert len({stage[c][q] for q in ex}) == 1
         chain_st = [stage[c][q] for q in range(l)]
         assert all(0 <= t < S for t in chain_st) and chain_st == sorted(set(chain_st)), (c, chain_st)
-        tf = stage[c][ks.index(2)]
+        tf = stage[c][ex[0]]
         assert 0 <= tf < S and all(t < tf for t in chain_st), (c, tf, chain_st)
         for q in range(d):
             if ks[q] == 1:
@@ -265,8 +301,9 @@ def emit(name, ident, out, NP=2):
     parts, cost = split_rows(sh, NP)
     half_of_row = [next(pi for pi, rows in enumerate(parts) if r in rows) for r in range(BR)]
     col_stage, cost2 = schedule_stages(cols_desc, half_of_row, NP, maxcd)
-    out.append("// %s: sz=%d, %dx%d blocks, %d circulants; %d parts %s; VN stage cost %d in chain order, %d scheduled (ideal %d)" %
-               (name, sz, BR, BC, sum(deg), NP, parts, cost, cost2, sum(deg) // NP))
+    merged = (-cost + 999) // 1000
+    out.append("// %s: sz=%d, %dx%d blocks, %d circulants; %d parts %s: %d edges share their variable's executor thread; VN stage cost %d in chain order, %d scheduled (ideal %d)" %
+               (name, sz, BR, BC, sum(deg), NP, parts, merged, cost + 1000 * merged, cost2, sum(deg) // NP))
     out.append("struct %s {" % ident)
     out.append("    static constexpr const char *name = \"%s\";" % name)
     out.append("    static constexpr int SZ = %d, BR = %d, BC = %d, NEDGE = %d, MAXD = %d, MAXCD = %d, NP = %d, HR = %d;" %
@@ -303,6 +340,9 @@ def emit(name, ident, out, NP=2):
 # fits two CTAs per SM next to the staging row --, executor = the column's first block row (mostly identity circulants);
 # VNC2T: longest chains (72 slots); VNC1: no chains at all, one stage, 112 slots (no room for a staging row).
 PLANS = [(2, True, 92, "top", False, 3, "VNC2"), (2, True, 72, "top", True, 1, "VNC2T"), (1, True, 112, "zero", True, 1, "VNC1")]
+import os as _os
+if _os.environ.get("QC_EXTRA_SEEDS"):        # plan lottery for A/B builds: QC_EXTRA_SEEDS="5 6 7" adds VNC2S5, VNC2S6, ...
+    PLANS = PLANS + [(2, True, 92, "top", False, int(x), "VNC2S" + x) for x in _os.environ["QC_EXTRA_SEEDS"].split()]
 
 
 def main():
