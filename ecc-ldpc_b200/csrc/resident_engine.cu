@@ -18,15 +18,19 @@
 //     (Orig.hs:73-78); leave-one-out reduction with the reference's min' operator (one FMNMX.XORSIGN each) in a
 //     binary tree; ne' = -3/4 * (reduction of the others), in place.
 //   * vote: barrier.red.or over the frame's threads = "syndrome all zero?"  (Orig.hs:68-69).
-//   * variable phase (Orig.hs:95-98): the right fold ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in place in
-//     smem, one link per stage from the innermost outwards.  Within a stage every address is touched by exactly
-//     one thread; a barrier separates stages; which link of which column runs in which stage is scheduled offline
-//     (tools/gen_qc_tables.py) so that the parts carry equal work in every stage.  Same association as the
-//     reference, so the fp64 instance reproduces the reference bit for bit.
-//     A stage issues all its loads before its first store (the accesses are ordered volatile asm).
-//   * last-link fold (min-sum): the thread that executes the LAST link of a column's chain finishes the new posterior
-//     of that variable and owns one of its edges, so it keeps x = ne' + mu and the sign of mu for that edge in
-//     registers: 44 of the 156 check-phase loads of an iteration never happen.
+//   * variable phase (Orig.hs:95-98): the right fold ne'[m1] + (ne'[m2] + ... (ne'[mk] + L_j)) is built in smem with the
+//     reference's operands, order and roundings by a PLAN made offline (tools/gen_qc_tables.py; VnPlan in
+//     resident_kernel.cuh): at most one chain link per column (load the running value, apply the own message, store);
+//     every other non-final edge is a singleton -- its thread stores the message into a slot of its own right behind the
+//     row's tree in the CHECK phase, where the store overlaps ALU-bound work --; the column's executor thread loads the
+//     chain value (or negL) and the column's slots and folds them in chain order, and folds edges of the same variable
+//     that it owns itself (same part, same shift) straight from registers.  2 stages + the vote = 3 barriers per
+//     iteration (the original one-link-per-stage schedule: 7).  Within a stage every address is touched by exactly one
+//     thread; a stage issues all its loads before its first store (the accesses are ordered volatile asm).  Same
+//     association as the reference, so the fp64 instance reproduces the reference bit for bit under every plan.
+//   * last-link fold (min-sum): the executor finishes the new posterior of its variable and owns one (or more) of its
+//     edges, so it keeps x = ne' + mu and the sign of mu for those edges in registers: 56 of the 156 check-phase loads of
+//     an iteration never happen.
 //   * early exit per frame; frames are handed out by an atomic work counter (persistent CTAs); host-supplied frames:
 //     the NEXT frame's LLR row is fetched by one bulk copy (cp.async.bulk + mbarrier) while the current one decodes.
 //   * sum-product (float32) runs the same phases in the complement domain, with one shared copy of the degree-18 row

@@ -121,7 +121,7 @@ def schedule_stages(cols_desc, owner, NP, T, seed=1):
     return table, best // 1000
 
 
-def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exec_rule="any", shifts=None, long_chain=False):
+def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exec_rule="any", shifts=None, long_chain=False, balance_cn=False):
     """Variable-node plan with S stages (S < the maximum column degree).  Column c of degree d applies the FIRST
     l <= min(d-1, S-1) links of its chain (innermost first) one per stage as before; of the remaining steps one is the
     column's EXECUTOR and the others are SINGLETONS: a singleton's thread only stores its raw message into a slot of its
@@ -203,6 +203,10 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
             else:
                 w = 1
             L[t if t >= 0 else S][owner[cols_desc[c][q]]] += sign * w
+            if balance_cn and q not in ex:
+                # the posterior load of a non-executor edge in the check phase, and its address rotation (two ALU-pipe
+                # instructions in an ALU-bound phase) when the circulant is not an identity
+                L[S][owner[cols_desc[c][q]]] += sign * (1 + (2 if shifts[cols_desc[c][q]][c] != 0 else 0))
 
     def loads(ch):
         L = [[0] * NP for _ in range(S + 1)]                   # index S: the check phase (stage -1)
@@ -214,6 +218,8 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
         over = max(0, nslots - max_slots)
         # (a singleton's store overlaps the trees of the check phase, a chain link is two operations in a stage: at equal
         # stage cost prefer the plan with more singletons)
+        if balance_cn:        # the check phase ends in a barrier too (the vote): its busiest part counts like a stage's
+            return (over * 100000 - nslots * 400 + sum(max(row) for row in L) * 1000 + sum(max(row) - min(row) for row in L) * 10)
         return (over * 100000 - nslots * 400 + sum(max(row) for row in L[:S]) * 1000 + sum(max(row) - min(row) for row in L[:S]) * 10 +
                 (max(L[S]) - min(L[S])) * 10 + (max(max(row) for row in L[:S]) - min(max(row) for row in L[:S])))
 
@@ -321,7 +327,8 @@ def emit(name, ident, out, NP=2):
     # short-chain plans (see plan_short_chains): VN<S> with singleton stores in the variable stages, VNC<S> with the
     # singleton stores in the check phase
     for S, cn_single, max_slots, rule, long_chain, seed, tag in PLANS:
-        stage, kind, slot, nslot, L = plan_short_chains(cols_desc, half_of_row, NP, S, cn_single, max_slots, seed=seed, exec_rule=rule, shifts=sh, long_chain=long_chain)
+        stage, kind, slot, nslot, L = plan_short_chains(cols_desc, half_of_row, NP, S, cn_single, max_slots, seed=seed, exec_rule=rule.split("+")[0], shifts=sh,
+                                                        long_chain=long_chain, balance_cn=rule.endswith("+cn"))
         out.append("    // %s: %d stages%s, %d singleton slots; shared-memory operations per stage and part %s%s" %
                    (tag, S, ", singletons stored in the check phase" if cn_single else "", nslot, L[:S],
                     ", check phase %s" % L[S] if cn_single else ""))
@@ -343,6 +350,9 @@ PLANS = [(2, True, 92, "top", False, 3, "VNC2"), (2, True, 72, "top", True, 1, "
 import os as _os
 if _os.environ.get("QC_EXTRA_SEEDS"):        # plan lottery for A/B builds: QC_EXTRA_SEEDS="5 6 7" adds VNC2S5, VNC2S6, ...
     PLANS = PLANS + [(2, True, 92, "top", False, int(x), "VNC2S" + x) for x in _os.environ["QC_EXTRA_SEEDS"].split()]
+if _os.environ.get("QC_EXTRA_CN"):           # ... QC_EXTRA_CN="1 2": VNC2B1, VNC2B2 balance the check phase too; VNC2A1...: any executor
+    PLANS = PLANS + [(2, True, 92, "top+cn", False, int(x), "VNC2B" + x) for x in _os.environ["QC_EXTRA_CN"].split()]
+    PLANS = PLANS + [(2, True, 92, "any+cn", False, int(x), "VNC2A" + x) for x in _os.environ["QC_EXTRA_CN"].split()]
 
 
 def main():

@@ -39,6 +39,9 @@ REPORTS = [
 def main():
     for stem, out, title, cmd in REPORTS:
         rep = os.path.join(EV, stem + ".ncu-rep")
+        if not os.path.exists(rep):
+            print("absent (other part of the evidence run), kept:", out)
+            continue
         md = subprocess.run([sys.executable, MD, rep, title, cmd], capture_output=True, text=True)
         if md.returncode:
             print("FAILED", stem, md.stderr[-500:])
@@ -47,13 +50,15 @@ def main():
     launch_md(os.path.join(EV, "launches_bench.csv"), "ncu launch list, round 2 kernels: bench.py",
               "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu",
               os.path.join(PR, "r02_launches_bench.md"))
-    launch_md(os.path.join(EV, "launches_stream.csv"), "ncu launch list, round 2 kernels: STREAM engine, decodes of 8192 frames jpl.4096.4.5 min-sum",
-              "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 100 --csv python tools/stream_probe.py 8192",
-              os.path.join(PR, "r02_launches_stream.md"))
+    if os.path.exists(os.path.join(EV, "launches_stream.csv")):
+      launch_md(os.path.join(EV, "launches_stream.csv"), "ncu launch list, round 2 kernels: STREAM engine, decodes of 8192 frames jpl.4096.4.5 min-sum",
+                "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 100 --csv python tools/stream_probe.py 8192",
+                os.path.join(PR, "r02_launches_stream.md"))
     for a, b in (("launches_bench.csv", "r02_launches_bench.csv"), ("launches_stream.csv", "r02_launches_stream.csv"),
                  ("bench_1gpu.json", "r02_bench_1gpu.json"), ("bench_reference.json", "r02_bench_reference.json"),
                  ("plain_bench_short.json", "r02_bench_short_for_launch_list.json")):
-        shutil.copy(os.path.join(EV, a), os.path.join(PR, b))
+        if os.path.exists(os.path.join(EV, a)):
+            shutil.copy(os.path.join(EV, a), os.path.join(PR, b))
     # traffic.json: only if the capture was taken from the library that is in the tree now
     import hashlib
     sys.path.insert(0, ROOT)
