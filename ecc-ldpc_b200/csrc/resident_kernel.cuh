@@ -74,8 +74,9 @@ template <class C0> struct VnPlanSel<WithPlan<C0, VnNone>, void> { typedef VnLeg
 template <class C> using VnPlan = typename VnPlanSel<C>::type;
 // Which plan serves which instance.  RES_VN_PLAN (default VNC2, the measured best: profiles/r02_vn_plans.md) for the
 // throughput and message-tap instances -- float32 min-sum, float32 sum-product, float64 --, each overridable
-// (RES_VN_PLAN_MIN / _SPA / _F64); the four-part latency instances keep the original schedule unless RES_VN_PLAN_LAT names
-// a plan (measured: no difference, 43 us per 20-iteration frame either way).  RES_VN_LEGACY: original schedule everywhere.
+// (RES_VN_PLAN_MIN / _SPA / _F64); the four-part latency instances (one frame per SM: shared memory is no constraint) take
+// the one-stage plan VNC1 (RES_VN_PLAN_LAT; one-frame call through the mailbox, 20 iterations: min-sum 60 -> 57 us,
+// sum-product 121 -> 110 us).  RES_VN_LEGACY: original schedule everywhere.
 #ifndef RES_VN_PLAN
 #define RES_VN_PLAN VNC2
 #endif
@@ -88,6 +89,9 @@ template <class C> using VnPlan = typename VnPlanSel<C>::type;
 #endif
 #ifndef RES_VN_PLAN_F64
 #define RES_VN_PLAN_F64 RES_VN_PLAN
+#endif
+#ifndef RES_VN_PLAN_LAT
+#define RES_VN_PLAN_LAT VNC1
 #endif
 #endif
 // LAT: instance of resident_latency.cu

@@ -22,7 +22,7 @@ REPORTS = [
      "ncu --set full: RESIDENT min-sum kernel k_resident<WithPlan<QcJpl1024P2, VNC2>, float, 4, MINSUM, 2, false> (BASELINE config 2: jpl.1024.4.5, 16384 frames, four frames per CTA, all 20 iterations, Eb/N0 2.0 dB)",
      NCU + " -k regex:k_resident -s 3 -c 1 python tools/quick_bench.py 16384 jpl.1024.4.5 min"),
     ("prof_latency_min", "r02_ncu_latency_minsum.md",
-     "ncu --set full: latency instance k_resident<QcJpl4096P4, float, 1, MINSUM, 1, false> behind the mailbox (ONE frame = one CTA of 512 threads, 20 iterations, LLRs read from mapped host memory)",
+     "ncu --set full: latency instance k_resident<WithPlan<QcJpl4096P4, VNC1>, float, 1, MINSUM, 1, false> behind the mailbox (ONE frame = one CTA of 512 threads, 20 iterations, LLRs read from mapped host memory)",
      NCU + " -k regex:k_resident -s 4 -c 1 python tools/one_mailbox.py min 2.0 12"),
     ("prof_stream_cn", "r02_ncu_stream_cn.md",
      "ncu --set full: STREAM check-node kernel k_cn_tma<float, MINSUM, 18, 2> (jpl.4096.4.5, 8192 frames, one iteration)",
@@ -72,7 +72,7 @@ def main():
                                "profiles/r02_ncu_resident_minsum.md"])
     else:
         print("traffic.json NOT written: the capture is of other kernel sources (%s... vs %s...)" % (want[:12], have[:12]))
-    for eng, pats in (("resident", ["QcJpl4096P2ENS2_4VNC2EEEfLi1ELi1ELi2ELb0", "QcJpl4096P2ENS2_4VNC2EEEfLi1ELi0ELi2ELb0", "QcJpl4096P4ENS_6VnNoneEEEfLi1ELi1ELi1ELb0"]),
+    for eng, pats in (("resident", ["QcJpl4096P2ENS2_4VNC2EEEfLi1ELi1ELi2ELb0", "QcJpl4096P2ENS2_4VNC2EEEfLi1ELi0ELi2ELb0", "QcJpl4096P4ENS2_4VNC1EEEfLi1ELi1ELi1ELb0"]),
                       ("stream", ["k_cn_tmaIfLi1ELi18ELi2", "k_vn_tmaIfLi4"]), ("onchip", ["k_onchipIfLi1ELi4ELb1ELi4"])):
         txt = "".join(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_summary.py"), p, "3"], capture_output=True, text=True).stdout for p in pats)
         open(os.path.join(PR, "r02_sass_%s.txt" % eng), "w").write(
