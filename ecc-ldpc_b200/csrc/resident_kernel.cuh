@@ -224,6 +224,15 @@ template <class C, typename T> struct Lay {
 #ifndef RES_SPA_LOG2
 #define RES_SPA_LOG2 1
 #endif
+#ifndef RES_SPA_STAGGER_NS
+#define RES_SPA_STAGGER_NS 0
+#endif
+#ifndef RES_SPA_REORDER
+#define RES_SPA_REORDER 1
+#endif
+#ifndef RES_MIN_STAGGER_NS
+#define RES_MIN_STAGGER_NS 0
+#endif
 __device__ __forceinline__ float spa_compl2(float x2) { return mufu_rcp(fmaf(mufu_ex2(fabsf(x2)), 0.5f, 0.5f)); }
 __device__ __forceinline__ float spa_mag2(float c) { return fminf(mufu_lg2(2.0f - c) - mufu_lg2(c), SPA_CAP_LG2); }
 template <typename T, int ALGO> struct Units {
@@ -422,6 +431,17 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
     constexpr int BLK = C::SZ * sizeof(float), D = C::MAXD, NB = BigRows<C>::NB;
     static_assert(BigRows<C>::uniform(), "parts must carry the same number of maximum-degree rows");
     uint32_t unsat = 0;
+#if RES_SPA_STAGGER_NS > 0
+    // experiment: the two warps of a frame that share a scheduler leave the barrier in lockstep and hit the XU pipe with
+    // their MUFU bursts at the same time; hold one of them back by a fraction of a row
+    if ((((threadIdx.x % (C::NP * C::SZ)) >> 5) & 4) != 0) __nanosleep(RES_SPA_STAGGER_NS);
+#endif
+    // RES_SPA_REORDER: the two warps of a frame that share a scheduler (warps w and w + 4) leave the barrier in lockstep and
+    // would hit the XU pipe with their MUFU bursts at the same time, leaving it idle while both are in their trees.  The
+    // upper four warps therefore take the small rows LAST instead of first: a third of a big row's work as a phase offset,
+    // at no cost (measured with a sleep first: 0 / 100 / 250 / 500 ns of delay: 8.29 / 8.31 / 8.35 / 8.54 Gbit/s).
+    const bool late = RES_SPA_REORDER && ((((threadIdx.x % (C::NP * C::SZ)) >> 5) & 4) != 0);
+    auto small_rows = [&]() {
     dispatch_index<0, C::NP>(h, [&](auto hi) {
         constexpr int H = decltype(hi)::value;
         static_for<C::HR>([&](auto qi) {
@@ -449,6 +469,8 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
             }
         });
     });
+    };
+    if (!late) small_rows();
 #pragma unroll 1
     for (int j = 0; j < NB; j++) {
         float xs[D];
@@ -496,6 +518,7 @@ __device__ __forceinline__ uint32_t cn_phase_spa_looped(float (&ne)[QcMap<C>::NE
             });
         });
     }
+    if (late) small_rows();
     return unsat & F::SIGN;
 }
 
@@ -663,6 +686,9 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             if constexpr (H >= 0 && RES_VOTE_FIRST && ALGO == LDPC_B200_ALGO_MINSUM) {
                 unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_gather<C, T, H, ALGO, FOLD>(ne, fpar, P)) != 0;
             } else if constexpr (H >= 0) {
+#if RES_MIN_STAGGER_NS > 0
+                if ((wif & 4) != 0) __nanosleep(RES_MIN_STAGGER_NS);      // experiment: see RES_SPA_REORDER
+#endif
                 unsat = ((n == p.max_iters) ? synd_phase<C, T, H>(P) : cn_phase<C, T, H, ALGO, FOLD>(ne, fpar, P)) != 0;
             } else {
                 typename FB<T>::B u = 0;
