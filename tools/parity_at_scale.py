@@ -18,7 +18,7 @@ CASES = [("jpl.4096.4.5", "min", 20, 5120, 3.25), ("jpl.4096.4.5", "spa", 20, 51
          ("jpl.1024.4.5", "spa", 20, 1280, 3.2), ("1920.1280.3.303", "min", 20, 1920, 1.8), ("1920.1280.3.303", "spa", 20, 1920, 1.5),
          ("moon.7.13", "spa", 20, 20, 2.0)]
 lib.init(0)
-print("# Parity at scale: float32 production engines vs float64 CPU restatement on identical LLRs (round 1)\n")
+print("# Parity at scale: float32 production engines vs float64 CPU restatement on identical LLRs (%s)\n" % (sys.argv[2] if len(sys.argv) > 2 else "round 1"))
 print("| code | algorithm | Eb/N0 dB | engine | frames | identical frames | fraction | differing bits in differing frames (mean) | iteration counts equal | GPU FER | CPU FER |")
 print("|---|---|---|---|---|---|---|---|---|---|---|")
 for name, algo, iters, n_tx, ebn0 in CASES:
