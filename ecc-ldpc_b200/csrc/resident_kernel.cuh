@@ -283,7 +283,8 @@ __device__ __forceinline__ void cn_store_single(T v, uint32_t P)
 // checks is unsatisfied by hard(lam).
 // FOLD (min-sum instances): for the edges that are the last link of their column's chain, the variable phase (or the
 // frame prologue) has already left x = ne + mu in the message register and the sign of mu in fpar[row], so the check
-// phase neither loads nor adds for them: 44 of the 156 shared-memory loads of an iteration disappear.
+// phase neither loads nor adds for them: 56 of the 156 shared-memory loads of an iteration disappear (44 columns, 12 of them
+// with two or more edges in their executor's hands).
 template <class C, typename T, int H, int ALGO, bool FOLD>
 __device__ __forceinline__ typename FB<T>::B cn_phase(T (&ne)[QcMap<C>::NEH], typename FB<T>::B (&fpar)[C::HR], uint32_t P)
 {
@@ -708,17 +709,31 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
             static_assert(STAGED || VnPlan<C>::NSLOT * C::SZ * sizeof(T) >= (N / 32) * sizeof(uint32_t), "no room to stage the packed decisions");
             uint32_t *obuf = STAGED ? reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + (size_t)(FPC - (bar - 1)) * Lay<C, T>::FS - Lay<C, T>::MUE + (size_t)(bar - 1) * N)
                                     : reinterpret_cast<uint32_t *>(const_cast<T *>(negL) + N);
-            unsigned int errs = 0;
-            for (int w = wif; w < W; w += WPF) {
-                const int j = 32 * w + lane;
-                unsigned int word = __ballot_sync(0xffffffffu, (conv ? mu[Lay<C, T>::mu_index(j)] : negL[j]) < (T)0);   // lam > 0 <=> -lam < 0
-                if (lane == 0) {
-                    if (p.done) obuf[w] = word;
-                    else if (p.bits) p.bits[(size_t)fi * W + w] = word;
-                    int lo = 32 * w;
-                    if (lo + 32 <= p.k_info) errs += __popc(word);
-                    else if (lo < p.k_info) errs += __popc(word & ((1u << (p.k_info - lo)) - 1u));
+            // Warp wif packs the WW consecutive words [wif * WW, (wif + 1) * WW): one ballot per word, lane q keeps word q, so the
+            // words leave with ONE coalesced store per warp and the error count is one popc per lane (this loop used to cost a
+            // frame ~600 instructions per warp -- three quarters of an iteration; profiles/r02_vn_plans.md).
+            constexpr int WW = W / WPF;
+            static_assert(W % WPF == 0 && WW <= 32, "decision words must split evenly over the warps of a frame");
+            unsigned int errs = 0, myword = 0;
+#pragma unroll
+            for (int q = 0; q < WW; q++) {
+                const int j = 32 * (wif * WW + q) + lane;
+                const unsigned int word = __ballot_sync(0xffffffffu, (conv ? mu[Lay<C, T>::mu_index(j)] : negL[j]) < (T)0);   // lam > 0 <=> -lam < 0
+                if (lane == q) myword = word;
+            }
+            if (lane < WW) {
+                const int w = wif * WW + lane;
+                if (p.done) obuf[w] = myword;
+                else if (p.bits) p.bits[(size_t)fi * W + w] = myword;
+                if (p.counters) {
+                    const int lo = 32 * w;
+                    if (lo + 32 <= p.k_info) errs = __popc(myword);
+                    else if (lo < p.k_info) errs = __popc(myword & ((1u << (p.k_info - lo)) - 1u));
                 }
+            }
+            if (p.counters) {
+                errs = __reduce_add_sync(0xffffffffu, errs);            // lane 0 carries the warp's count (summed up in k_resident)
+                if (lane != 0) errs = 0;
             }
             if (p.done) {
                 // mailbox: the packed decisions leave in full lines (the arrays are in mapped host memory: one PCIe write per
@@ -737,8 +752,10 @@ __device__ __forceinline__ void decode_frame(const ResidentParams &p, unsigned i
                 bool anyerr = bar_or(bar, TPF, errs != 0);
                 cnt.berr += errs;
                 if (tf == 0) { cnt.frames++; cnt.ferr += anyerr; cnt.iters += n; cnt.unconv += !conv; }
-            } else if (!p.early_exit) {
-                bar_sync(bar, TPF);          // snapshot reads of mu before the next stage-0 writes
+            } else {
+                // the decision reads of mu / negL above are done before anybody writes them again: the next stage-0 writes (no
+                // early exit) or the next frame's values (a warp packs words that other warps' threads will overwrite)
+                bar_sync(bar, TPF);
             }
         }
         if (n == p.max_iters || (done && p.early_exit)) break;
@@ -843,7 +860,20 @@ __global__ void __launch_bounds__(FPC * C::NP * C::SZ, MINB) k_resident(Resident
             const T *row = stage;
             if constexpr (STAGED) { mbar_wait(mbar, phase); phase ^= 1u; }
             else row = reinterpret_cast<const T *>(p.llr) + (size_t)f * N;     // warmed in L2 while the previous frame decoded
-            for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(row[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
+            if constexpr (RES_DUP) {
+                for (int j = tf; j < N; j += TPF) { T v = F::sub((T)0, Units<T, ALGO>::in(row[j])); negL[j] = v; put_mu(j, v); }   // 0 - L: never -0.0
+            } else {
+                // 16 bytes per access: the rows are 16-byte aligned (llr_bulk) and N is a multiple of 32
+                constexpr int VE = 16 / (int)sizeof(T);
+                struct alignas(16) V16 { T v[VE]; };
+                for (int j = tf * VE; j < N; j += TPF * VE) {
+                    V16 x = *reinterpret_cast<const V16 *>(row + j);
+#pragma unroll
+                    for (int q = 0; q < VE; q++) x.v[q] = F::sub((T)0, Units<T, ALGO>::in(x.v[q]));      // 0 - L: never -0.0
+                    *reinterpret_cast<V16 *>(negL + j) = x;
+                    *reinterpret_cast<V16 *>(mu + j) = x;
+                }
+            }
             bar_sync(bar, TPF);                 // the staging row has been read by everybody: it can take the next frame
             if (tf == 0) {
                 const unsigned int nxt = atomicAdd(p.work, 1u);

@@ -1214,3 +1214,36 @@ def test_code_outlives_its_handle_while_decoders_use_it(gpu_lib, builtin_codes, 
     dec.close(); dec.close()
     L.ldpc_b200_live_handles(C.byref(nc), C.byref(nd))
     assert (nc.value, nd.value) == base
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("code_name,F,algo", [("jpl.1024.4.5", 32768, "min"), ("jpl.4096.4.5", 8192, "min"), ("jpl.1024.4.5", 16384, "spa"),
+                                             ("1920.1280.3.303", 16384, "min")])
+def test_fallback_decisions_exact_at_scale(code_name, F, algo, gpu_lib, dcodes, builtin_codes):
+    """Far below the waterfall no frame converges, so every frame must come back as the hard decision of its CHANNEL values
+    (`n >= maxIterations -> orig_lam`, Orig.hs:68-71 / Min.hs:64-67): an exact known answer for tens of thousands of frames
+    per launch, independent of any restatement.  It is the case in which a frame's state is read at the very end of its life
+    -- while the persistent CTA is already taking in the next frame -- so it pins the hand-over between frames (a missing
+    barrier there showed up as 2 wrong frames in 16 384, inside the 99.9 % bar of the statistical tests)."""
+    code = builtin_codes[code_name]
+    W = (code.N + 31) // 32
+    n_tx = TX.get(code_name) or code.N
+    dec = gpu_lib.Decoder(dcodes[code_name], algo, "fp32", max_batch=F)
+    d_llr = gpu_lib.DeviceBuffer(F * code.N * 4)
+    d_bits = gpu_lib.DeviceBuffer(F * W * 4)
+    d_it = gpu_lib.DeviceBuffer(F * 4)
+    d_cv = gpu_lib.DeviceBuffer(F)
+    dec.generate_llr(d_llr.ptr, -1.0, code.K, n_tx, 77, 0, F)
+    dec.sync()
+    llr = d_llr.download(np.float32, (F, code.N))
+    for rep in range(3):                                   # the hand-over is a race if it is one: give it a few chances
+        d_bits.zero()
+        dec.decode_device(d_llr.ptr, d_bits.ptr, 20, F, early_exit=True, d_iters=d_it.ptr, d_conv=d_cv.ptr)
+        dec.sync()
+        bits = gpu_lib.unpack_bits(d_bits.download(np.uint32, (F, W)), code.N)
+        cv = d_cv.download(np.uint8, (F,))
+        it = d_it.download(np.int32, (F,))
+        stuck = cv == 0
+        assert stuck.mean() > 0.99 and (it[stuck] == 20).all()
+        assert np.array_equal(bits[stuck], (llr[stuck] > 0).astype(bits.dtype)), "a non-converged frame is not hard(orig_lam)"
+    dec.close()
