@@ -121,7 +121,7 @@ def schedule_stages(cols_desc, owner, NP, T, seed=1):
     return table, best // 1000
 
 
-def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exec_rule="any", shifts=None, long_chain=False, balance_cn=False):
+def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exec_rule="any", shifts=None, long_chain=False, balance_cn=False, iters=200000):
     """Variable-node plan with S stages (S < the maximum column degree).  Column c of degree d applies the FIRST
     l <= min(d-1, S-1) links of its chain (innermost first) one per stage as before; of the remaining steps one is the
     column's EXECUTOR and the others are SINGLETONS: a singleton's thread only stores its raw message into a slot of its
@@ -226,7 +226,7 @@ def plan_short_chains(cols_desc, owner, NP, S, cn_single, max_slots, seed=1, exe
     L = loads(choice)
     ns = slots(choice)
     best = cost_of(L, ns)
-    for it in range(200000):
+    for it in range(iters):
         c = rng.randrange(BC)
         new = random_assign(degs[c], c)
         if new is None:
